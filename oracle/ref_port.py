@@ -1,0 +1,55 @@
+"""fp32 torch/torchaudio port of the reference CPU feature path (TEST INFRASTRUCTURE — oracle/__init__.py).
+
+This is the CPU arm that ``bench.py`` times (``cpu_baseline`` and ``--impl reference``): the same
+torchaudio call sequence as reference dataset.py:38-56 (``MelSpectrogram`` per channel, ``torch.cat``,
+``AmplitudeToDB``), running on the host cores through torch's MKL/pocketfft ``torch.stft``.  The
+reference tree itself cannot travel to the GPU box, so this port is what runs there; in the build
+container it is checked bit-for-bit against the real ``dataset.audio_to_mel_spectrogram``
+(tests/golden/make_golden.py, tests/test_oracle.py).
+
+The FOA-IV part has no reference code; ``logmel_iv_port`` adds it with the same torch primitives
+(``torch.stft`` complex output) so the 7-channel CPU baseline does the same work as the GPU kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def audio_to_mel_spectrogram_port(waveform: torch.Tensor, sample_rate: int, n_fft: int, hop_length: int,
+                                  n_mels: int) -> torch.Tensor:
+    """dataset.py:27-58, same calls in the same order.  (C, N) fp32 -> (C, n_mels, T) fp32 dB."""
+    import torchaudio
+
+    mel_transform = torchaudio.transforms.MelSpectrogram(
+        sample_rate=sample_rate, n_fft=n_fft, hop_length=hop_length, n_mels=n_mels)
+    mel_specs = []
+    for channel_idx in range(waveform.shape[0]):
+        mel_specs.append(mel_transform(waveform[channel_idx:channel_idx + 1, :]))
+    mel = torch.cat(mel_specs, dim=0)
+    return torchaudio.transforms.AmplitudeToDB()(mel)
+
+
+def _fb(n_fft, sample_rate, n_mels):
+    import torchaudio
+
+    return torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, 0.0, float(sample_rate // 2), n_mels,
+                                                 sample_rate, norm=None, mel_scale="htk")
+
+
+def logmel_iv_port(waveform: torch.Tensor, sample_rate: int, n_fft: int, hop_length: int, n_mels: int,
+                   fb: torch.Tensor | None = None) -> torch.Tensor:
+    """7-channel FOA feature (7, n_mels, T) fp32 on the CPU: one batched torch.stft, power->mel->dB for
+    the 4 channels, IV from the complex spectra."""
+    if fb is None:
+        fb = _fb(n_fft, sample_rate, n_mels)
+    win = torch.hann_window(n_fft)
+    X = torch.stft(waveform, n_fft, hop_length, n_fft, win, center=True, pad_mode="reflect",
+                   normalized=False, onesided=True, return_complex=True)  # (4, F, T)
+    P = X.real * X.real + X.imag * X.imag
+    mel = torch.matmul(P.transpose(-1, -2), fb).transpose(-1, -2)
+    db = 10.0 * torch.log10(torch.clamp(mel, min=1e-10))
+    W = X[0]
+    I = (W.real.unsqueeze(0) * X[1:].real + W.imag.unsqueeze(0) * X[1:].imag)
+    E = 1e-8 + P[0] + P[1:].sum(0) / 3.0
+    iv = torch.matmul((I / E.unsqueeze(0)).transpose(-1, -2), fb).transpose(-1, -2)
+    return torch.cat([db, iv], dim=0)
