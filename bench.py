@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the SELD feature front-end hot path (BASELINE.json configs[1]).
+
+Step = one pass of the fused STFT + log-mel + IV kernel over a batch of 256 synthetic 60 s 4-channel 24 kHz
+clips per GPU (n_fft 1024, hop 480, 64 mel -> 7-channel features), inputs resident in HBM.
+Metric: audio clip-seconds per second, whole job (all ranks).  One JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+--impl reference times the reference's CPU implementation of the same path on the host cores (the torch /
+torchaudio call sequence of reference dataset.py:38-56, ported in oracle/ref_port.py because the reference
+tree cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, N_FFT, HOP, N_MELS, CH = 24000, 1024, 480, 64, 4
+CLIP_SECONDS = 60
+BYTES_PER_CLIP_SECOND = 4 * SR * CH + 7 * N_MELS * (SR // HOP) * 4  # 473 600
+METRIC, UNIT = "audio_clip_seconds_per_sec", "clip-s/s"
+WORKLOAD = ("configs[1]: batch of 256 synthetic 60 s 4-ch FOA clips @24 kHz per GPU -> 7-ch log-mel+IV, "
+            "n_fft 1024 / hop 480 / 64 mel")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_rate(seconds_budget: float, min_clips: int, seed: int = 1234):
+    """Time the reference's CPU feature path (oracle.ref_port, all host threads) on a bounded sample of the
+    same workload: 60 s 4-ch clips -> 7-ch log-mel+IV.  Returns (clip-s/s, cores, n_clips)."""
+    import torch
+
+    from oracle import ref_port
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(CH, SR * CLIP_SECONDS, generator=g)
+    fb = ref_port._fb(N_FFT, SR, N_MELS)
+    ref_port.logmel_iv_port(x, SR, N_FFT, HOP, N_MELS, fb)  # warm-up (MKL plan, thread pool)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        ref_port.logmel_iv_port(x, SR, N_FFT, HOP, N_MELS, fb)
+        n += 1
+        el = time.perf_counter() - t0
+        if n >= min_clips and el >= seconds_budget:
+            break
+    return n * CLIP_SECONDS / el, cores, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import ref_port
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    clips_per_step = args.ref_clips
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(CH, SR * CLIP_SECONDS, generator=g)
+    fb = ref_port._fb(N_FFT, SR, N_MELS)
+
+    def step():
+        for _ in range(clips_per_step):
+            ref_port.logmel_iv_port(x, SR, N_FFT, HOP, N_MELS, fb)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = args.steps * clips_per_step * CLIP_SECONDS / el
+    sample = f"{clips_per_step} x 60 s clips per step (bounded sample of the 256-clip batch), torch {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the CPU reference arm")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import seld_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N = args.clips, SR * CLIP_SECONDS
+    T = 1 + N // HOP
+
+    # synthetic shard of this rank, generated on the device (seed 1234 + rank), resident in HBM
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    audio = torch.empty((B, CH, N), dtype=torch.float32, device=dev)
+    audio.normal_(0.0, 0.1, generator=gen)
+    out = torch.empty((B, T, 7, N_MELS), dtype=torch.float32, device=dev)
+    stats = torch.zeros(2 * 7 * N_MELS, dtype=torch.float64, device=dev)
+    stat_frames = torch.full((B,), T - 1, dtype=torch.int32, device=dev)  # the frames SELDDataset keeps
+    plan = seld_b200.get_plan(N_FFT, HOP, N_MELS, SR, dev)
+
+    def step():
+        plan.run(audio, mode="logmel_iv", out=out, stats=stats, stat_frames=stat_frames)
+        if world > 1:  # the path's only collective: scaler partials (sum, sum of squares), ~7 KB fp64
+            dist.all_reduce(stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        stats.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    stats.zero_()
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clip_s_per_step = B * CLIP_SECONDS
+    value = world * clip_s_per_step * args.steps / (total_ms / 1e3)
+
+    # dominant kernel (the only kernel of the step): per-launch duration from the same events; with N > 1
+    # the tiny all-reduce sits between launches, so N = 1 is the clean roofline figure
+    kern_ms = total_ms / args.steps
+    peak, peak_src = peaks()
+    achieved = BYTES_PER_CLIP_SECOND * clip_s_per_step / (kern_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "seld::features_kernel<32,IV,STATS>",
+                "algorithmic_bytes_per_launch": BYTES_PER_CLIP_SECOND * clip_s_per_step}
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tfile):
+        try:
+            roofline["traffic"] = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D + kernel + D2H every step ----
+    e2e = None
+    if not args.no_e2e:
+        from seld_b200.features import extract_features_host
+        h_audio = torch.empty((B, CH, N), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((B, T, 7, N_MELS), dtype=torch.float32, pin_memory=True)
+        chunk = 16
+        for b0 in range(0, B, chunk):  # fill the pinned buffer from the device shard (not timed)
+            h_audio[b0:b0 + chunk].copy_(audio[b0:b0 + chunk])
+        torch.cuda.synchronize()
+        extract_features_host(h_audio, h_out, plan, mode="logmel_iv")  # warm-up (staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            extract_features_host(h_audio, h_out, plan, mode="logmel_iv")
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": world * clip_s_per_step * args.e2e_steps / el, "unit": UNIT,
+               "h2d_bytes_per_step": h_audio.numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4,
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * el / args.e2e_steps,
+               "api": "seld_b200.features.extract_features_host (pinned host in/out, 3-stream chunked pipeline)",
+               "check": float(h_out[0, 0, 0, 0])}
+        del h_audio, h_out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, n = cpu_reference_rate(args.cpu_seconds, 4)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} x 60 s 4-ch clips -> 7-ch log-mel+IV, oracle/ref_port.py (torch.stft/MKL, {cores} threads)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu": B, "clip_seconds": CLIP_SECONDS,
+                       "l2": "inputs 5.9 GB per step >> 126 MB L2 (no flush needed)",
+                       "collective": "all_reduce(fp64 scaler partials, 7 KB) per step" if world > 1 else "none (1 GPU)",
+                       "timing": "CUDA events on the launch stream, max over ranks"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

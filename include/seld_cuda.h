@@ -1,0 +1,124 @@
+/* libseld_cuda — C ABI of the B200-native SELD feature front-end (hand-written sm_100a kernels).
+ *
+ * The reference (Zeudon/sound-event-localization-detection) has no FFI: its boundary for this path is the
+ * set of plain Python callables in dataset.py / smrl_seld_gaussian.py.  Each entry point below names the
+ * reference function it replaces.  The Python host layer (sound-event-localization-detection_b200/*.py)
+ * binds these with ctypes and re-exposes the reference's names and signatures; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - All d_* pointers are DEVICE pointers owned by the caller (PyTorch allocates them); h_* are host
+ *    pointers.  The library never allocates or frees caller memory; a plan owns only its constant tables.
+ *  - Every compute call is asynchronous and stream-ordered on `stream` (a cudaStream_t passed as void*;
+ *    NULL = legacy default stream).  No hidden synchronisation, no host allocation on the hot calls.
+ *  - Return value: 0 = OK, negative = seld_status.  Nothing aborts or throws across the boundary;
+ *    seld_last_error() returns a thread-local message for the last failing call on this thread.
+ *  - There is no CPU fallback: without a CUDA device every compute call returns SELD_ERR_CUDA.
+ */
+#ifndef SELD_CUDA_H
+#define SELD_CUDA_H
+
+#include <stdint.h>
+
+#if defined(_WIN32)
+#define SELD_API
+#else
+#define SELD_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum seld_status {
+    SELD_OK = 0,
+    SELD_ERR_BAD_ARG = -1,
+    SELD_ERR_UNSUPPORTED = -2, /* e.g. n_fft other than 960 / 1024, n_mels > 64 */
+    SELD_ERR_CUDA = -3,
+    SELD_ERR_ALLOC = -4
+} seld_status;
+
+typedef struct seld_plan seld_plan;
+
+/* feature sets (seld_features `mode`) */
+#define SELD_MODE_LOGMEL 0     /* C log-mel channels             (reference dataset.py:27-58)            */
+#define SELD_MODE_LOGMEL_IV 1  /* 4 log-mel + 3 FOA intensity     (north_star kernel 2; not in reference) */
+#define SELD_MODE_LOGMEL_GCC 2 /* 4 log-mel + 6 GCC-PHAT x n_mels (north_star kernel 3; not in reference) */
+
+SELD_API int seld_version(void);
+SELD_API const char* seld_last_error(void);
+
+/* Number of STFT frames torch.stft(center=True) produces: 1 + n_samples / hop
+ * (torchaudio/functional/functional.py:123-134 via reference dataset.py:49). */
+SELD_API int64_t seld_num_frames(int64_t n_samples, int hop);
+
+/* Output channels of a mode for C input channels (C, 7, 10). */
+SELD_API int seld_out_channels(int mode, int n_channels);
+
+/* Build the constant tables of one (n_fft, hop, n_mels) configuration on `device`.
+ * Replaces the per-call construction in reference dataset.py:38-43
+ * (torchaudio.transforms.MelSpectrogram: Hann window + HTK filterbank).
+ *   h_window : n_fft floats, the analysis window (torch.hann_window(n_fft), float32)
+ *   h_fb     : (n_fft/2+1, n_mels) row-major float32 filterbank (melscale_fbanks(...))
+ * n_fft in {960, 1024}; n_mels <= 64. */
+SELD_API int seld_plan_create(seld_plan** plan, int device, int n_fft, int hop, int n_mels, const float* h_window,
+                     const float* h_fb);
+SELD_API int seld_plan_destroy(seld_plan* plan);
+
+/* Fused framing + window + real FFT + power + mel + 10*log10 (+ IV | + GCC-PHAT).
+ * Replaces reference dataset.py:27-58 audio_to_mel_spectrogram for a whole batch of clips.
+ *   d_audio      : float32, clip b channel c sample n at d_audio[b*clip_stride + c*chan_stride + n]
+ *   d_lengths    : int64[B] valid samples per clip, or NULL (all = n_samples); each must be > n_fft/2
+ *   d_out        : float32 (B, T_out, C_out, n_mels), frame-major ("TCM") — the layout the reference's
+ *                  models consume after dataset.py:303; rows t >= 1 + len_b/hop are written as 0
+ *   T_out        : frame capacity per clip (>= seld_num_frames(max length))
+ *   C_out        : channel count of d_out (>= c_off + seld_out_channels(mode, C))
+ *   c_off        : first output channel to write
+ *   d_stats      : optional float64[2 * C_out * n_mels]: the call ADDS per-feature sum and sum of squares
+ *                  of the values it writes for frames t < d_stat_frames[b] (or all valid frames when
+ *                  d_stat_frames is NULL) — the normalisation-scaler partials
+ *   d_spec       : optional float32 complex (B, C, T_out, n_fft/2+1) dump of the STFT (parity tests)
+ */
+SELD_API int seld_features(seld_plan* plan, int mode, const float* d_audio, int64_t clip_stride, int64_t chan_stride,
+                  int64_t n_samples, const int64_t* d_lengths, int B, int C, float* d_out, int64_t T_out,
+                  int C_out, int c_off, double* d_stats, const int32_t* d_stat_frames, float* d_spec,
+                  void* stream);
+
+/* (x - mean) * inv_std in place over (rows, n_feat) float32; mean/inv_std float32[n_feat].
+ * The scaler apply step. */
+SELD_API int seld_scaler_apply(float* d_x, int64_t rows, int n_feat, const float* d_mean, const float* d_inv_std,
+                      void* stream);
+
+/* Dense SELD grid labels (T, cells, classes) float32 for a batch of label tensors.
+ * Replaces reference dataset.py:60-119 metadata_to_labels and smrl_seld_gaussian.py:397-534
+ * augment_with_gaussian_noise.  The host parses the CSV exactly like the reference (pandas + int()) and
+ * hands over compact event tables; the kernels do the dense encoding.
+ *
+ * seld_labels_fill   : every (t, cell) <- one-hot background (class n_classes-1), i.e. the state the
+ *                      reference reaches for cells with no event (dataset.py:114-117); rows total.
+ * seld_labels_paint  : n_events events; event e covers rows [row0[e], row1[e]) of d_out (absolute row
+ *                      index = frame index inside the concatenated (rows, cells, classes) tensor) and
+ *                      class cls[e] (already wrapped to [0, n_classes)).
+ *                      point events : cell[e] >= 0 is the single grid cell (utils.py:77-90 polar_to_grid)
+ *                      region events: cell[e] < 0; centre[e] = (azimuth + noise, elevation + noise) in
+ *                      float64 and every cell whose centre passes the reference's +-2 sigma test
+ *                      (smrl_seld_gaussian.py:474-518, same float64 operations and <= comparisons) is painted.
+ *                      Painting sets (t, cell, cls) = 1 and clears the background class of that cell unless
+ *                      some event of the cell has cls == n_classes-1 (then it stays 1, as in the reference).
+ *   d_events : int32 (n_events, 4) rows {row0, row1, cls, cell}
+ *   d_centres: float64 (n_events, 2) or NULL when there are no region events
+ */
+SELD_API int seld_labels_fill(float* d_out, int64_t rows, int cells, int n_classes, void* stream);
+SELD_API int seld_labels_paint(float* d_out, int64_t rows, int I, int J, int n_classes, const int32_t* d_events,
+                      const double* d_centres, int n_events, double sigma_az, double sigma_el, void* stream);
+
+/* Window/batch assembly (reference dataset.py:267-330 _create_windows + __getitem__, for a batch):
+ * out[w, f, :] = src[start[w] + f, :] for start[w] + f < rows, else `pad_row` (row_len floats; zeros for
+ * features, one-hot background for labels).  src (rows, row_len), out (n_win, win_len, row_len). */
+SELD_API int seld_window_gather(const float* d_src, int64_t rows, int64_t row_len, const int64_t* d_starts, int n_win,
+                       int win_len, const float* d_pad_row, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELD_CUDA_H */

@@ -1,0 +1,195 @@
+// K4: dense SELD grid label encoder (fill + paint), K6: window/batch gather, scaler apply.
+//
+// Reference semantics reproduced (bit-exact):
+//   dataset.py:84            labels = zeros(T, I*J, M)
+//   dataset.py:100-111       labels[t, cell, class] = 1.0 for the 5 frames of each CSV row
+//   dataset.py:114-117       labels[t, cell, M-1] = 1.0 for every (t, cell) that no row touched
+//   smrl_seld_gaussian.py:474-518  region variant: every cell whose centre is inside the +-2 sigma rectangle
+//   dataset.py:267-317       windows [50k, 50k+250) with zero / background padding of the tail
+// "fill" writes the no-event state everywhere at HBM write bandwidth; "paint" then touches only the few
+// (row, cell) pairs that events cover: pass 0 clears the background class, pass 1 sets the event class (a
+// class M-1 event therefore leaves the background at 1, like the reference).
+#include "seld_common.h"
+
+namespace seld {
+
+// ---- fill: period-M pattern (0,...,0,1), 128-bit stores --------------------------------------------
+__global__ void labels_fill_vec4(float4* __restrict__ out, long long n_vec, int M) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vec) return;
+    int r = int((4 * i) % M);                         // class index of the first lane element
+    const int step = int((4 * stride) % M);
+    for (; i < n_vec; i += stride) {
+        int r1 = r + 1; if (r1 >= M) r1 -= M;
+        int r2 = r1 + 1; if (r2 >= M) r2 -= M;
+        int r3 = r2 + 1; if (r3 >= M) r3 -= M;
+        float4 v = make_float4(r == M - 1 ? 1.f : 0.f, r1 == M - 1 ? 1.f : 0.f, r2 == M - 1 ? 1.f : 0.f,
+                               r3 == M - 1 ? 1.f : 0.f);
+        __stcs(out + i, v);                            // streaming store: written once, not re-read here
+        r += step; if (r >= M) r -= M;
+    }
+}
+
+__global__ void labels_fill_scalar(float* __restrict__ out, long long n, int M) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (i % M == M - 1) ? 1.f : 0.f;
+}
+
+// ---- paint ---------------------------------------------------------------------------------------
+// Region membership, float64, same operations in the same order as smrl_seld_gaussian.py:474-514.
+// __d*_rn intrinsics forbid FMA contraction so every step rounds like CPython's float arithmetic.
+__device__ __forceinline__ bool cell_in_region(int gi, int gj, int I, int J, double c_az, double c_el, double two_s_az,
+                                               double two_s_el) {
+    const double el_min = fmax(__dsub_rn(c_el, two_s_el), -90.0);
+    const double el_max = fmin(__dadd_rn(c_el, two_s_el), 90.0);
+    const double cell_el = __dadd_rn(-90.0, __dmul_rn((double)gi + 0.5, 180.0 / (double)I));
+    const double cell_az = __dadd_rn(-180.0, __dmul_rn((double)gj + 0.5, 360.0 / (double)J));
+    double diff = __dsub_rn(cell_az, c_az);
+    for (int it = 0; it < 64 && diff > 180.0; ++it) diff = __dsub_rn(diff, 360.0);
+    for (int it = 0; it < 64 && diff < -180.0; ++it) diff = __dadd_rn(diff, 360.0);
+    return (fabs(diff) <= two_s_az) && (el_min <= cell_el) && (cell_el <= el_max);
+}
+
+// one CTA per event; pass 0: background <- 0, pass 1: class <- 1
+__global__ void labels_paint_kernel(float* __restrict__ out, long long rows, int I, int J, int M,
+                                    const int4* __restrict__ events, const double2* __restrict__ centres,
+                                    double two_s_az, double two_s_el, int pass) {
+    const int4 ev = events[blockIdx.x];  // {row0, row1, cls, cell}
+    const long long row0 = ev.x, row1 = ev.y;
+    if (row1 <= row0) return;
+    const int cells = I * J;
+    const int col = pass == 0 ? M - 1 : ev.z;
+    const float val = pass == 0 ? 0.f : 1.f;
+    if (ev.w >= 0) {
+        for (long long r = row0 + threadIdx.x; r < row1; r += blockDim.x)
+            out[(r * cells + ev.w) * M + col] = val;
+        return;
+    }
+    const double2 c = centres[blockIdx.x];
+    for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+        if (!cell_in_region(cell / J, cell % J, I, J, c.x, c.y, two_s_az, two_s_el)) continue;
+        for (long long r = row0; r < row1; ++r) out[(r * cells + cell) * M + col] = val;
+    }
+}
+
+// ---- window gather -------------------------------------------------------------------------------
+template <typename V>
+__global__ void window_gather_kernel(const V* __restrict__ src, long long rows, long long row_len,
+                                     const long long* __restrict__ starts, int win_len,
+                                     const V* __restrict__ pad_row, V* __restrict__ out, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long j = i % row_len;
+        const long long wf = i / row_len;
+        const long long f = wf % win_len;
+        const long long w = wf / win_len;
+        const long long r = starts[w] + f;
+        out[i] = (r >= 0 && r < rows) ? src[r * row_len + j] : pad_row[j];
+    }
+}
+
+template <typename V>
+__global__ void scaler_apply_kernel(V* __restrict__ x, long long total, int n_feat_v, const V* __restrict__ mean,
+                                    const V* __restrict__ inv_std);
+
+template <>
+__global__ void scaler_apply_kernel<float4>(float4* __restrict__ x, long long total, int n_feat_v,
+                                            const float4* __restrict__ mean, const float4* __restrict__ inv_std) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int f = int(i % n_feat_v);
+        float4 v = x[i];
+        const float4 m = __ldg(mean + f), s = __ldg(inv_std + f);
+        v.x = (v.x - m.x) * s.x; v.y = (v.y - m.y) * s.y; v.z = (v.z - m.z) * s.z; v.w = (v.w - m.w) * s.w;
+        x[i] = v;
+    }
+}
+
+template <>
+__global__ void scaler_apply_kernel<float>(float* __restrict__ x, long long total, int n_feat_v,
+                                           const float* __restrict__ mean, const float* __restrict__ inv_std) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int f = int(i % n_feat_v);
+        x[i] = (x[i] - __ldg(mean + f)) * __ldg(inv_std + f);
+    }
+}
+
+static int grid_for(long long work, int block, int device_sms) {
+    long long g = (work + block - 1) / block;
+    long long cap = (long long)device_sms * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static int current_sms() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch_labels_fill(float* out, long long rows, int cells, int M, cudaStream_t st) {
+    const long long n = rows * cells * M;
+    if (n == 0) return SELD_OK;
+    const int sms = current_sms();
+    if (aligned16(out) && n % 4 == 0) {
+        labels_fill_vec4<<<grid_for(n / 4, 256, sms), 256, 0, st>>>(reinterpret_cast<float4*>(out), n / 4, M);
+    } else {
+        labels_fill_scalar<<<grid_for(n, 256, sms), 256, 0, st>>>(out, n, M);
+    }
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+int launch_labels_paint(float* out, long long rows, int I, int J, int M, const int* events, const double* centres,
+                        int n_events, double sigma_az, double sigma_el, cudaStream_t st) {
+    if (n_events == 0) return SELD_OK;
+    const double two_az = 2 * sigma_az, two_el = 2 * sigma_el;  // the reference's `2 * sigma_*`
+    for (int pass = 0; pass < 2; ++pass) {
+        labels_paint_kernel<<<n_events, 128, 0, st>>>(out, rows, I, J, M, reinterpret_cast<const int4*>(events),
+                                                       reinterpret_cast<const double2*>(centres), two_az, two_el,
+                                                       pass);
+        SELD_CUDA_TRY(cudaGetLastError());
+    }
+    return SELD_OK;
+}
+
+int launch_window_gather(const float* src, long long rows, long long row_len, const long long* starts, int n_win,
+                         int win_len, const float* pad_row, float* out, cudaStream_t st) {
+    const long long total = (long long)n_win * win_len * row_len;
+    if (total == 0) return SELD_OK;
+    const int sms = current_sms();
+    if (row_len % 4 == 0 && aligned16(src) && aligned16(out) && aligned16(pad_row)) {
+        window_gather_kernel<float4><<<grid_for(total / 4, 256, sms), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(src), rows, row_len / 4, starts, win_len,
+            reinterpret_cast<const float4*>(pad_row), reinterpret_cast<float4*>(out), total / 4);
+    } else {
+        window_gather_kernel<float><<<grid_for(total, 256, sms), 256, 0, st>>>(src, rows, row_len, starts, win_len,
+                                                                                 pad_row, out, total);
+    }
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+int launch_scaler_apply(float* x, long long rows, int n_feat, const float* mean, const float* inv_std,
+                        cudaStream_t st) {
+    const long long total = rows * n_feat;
+    if (total == 0) return SELD_OK;
+    const int sms = current_sms();
+    if (n_feat % 4 == 0 && aligned16(x) && aligned16(mean) && aligned16(inv_std)) {
+        scaler_apply_kernel<float4><<<grid_for(total / 4, 256, sms), 256, 0, st>>>(
+            reinterpret_cast<float4*>(x), total / 4, n_feat / 4, reinterpret_cast<const float4*>(mean),
+            reinterpret_cast<const float4*>(inv_std));
+    } else {
+        scaler_apply_kernel<float><<<grid_for(total, 256, sms), 256, 0, st>>>(x, total, n_feat, mean, inv_std);
+    }
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+}  // namespace seld

@@ -1,0 +1,205 @@
+"""Feature front-end: host side of the fused STFT + log-mel (+ IV | + GCC-PHAT) kernels.
+
+Mirrors the reference's ``audio_to_mel_spectrogram`` (dataset.py:27-58) — same name, arguments and
+result shape — on top of ``seld_features`` in libseld_cuda.  PyTorch is used for device memory, streams
+and the two constant tables (window, filterbank); all arithmetic on the audio happens in the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import SELD_MODE_LOGMEL, SELD_MODE_LOGMEL_GCC, SELD_MODE_LOGMEL_IV
+
+MODES = {"logmel": SELD_MODE_LOGMEL, "logmel_iv": SELD_MODE_LOGMEL_IV, "foa_iv": SELD_MODE_LOGMEL_IV,
+         "logmel_gcc": SELD_MODE_LOGMEL_GCC, "mic_gcc": SELD_MODE_LOGMEL_GCC}
+
+
+def hann_window(n_fft: int) -> torch.Tensor:
+    """The window torchaudio.transforms.MelSpectrogram uses (torchaudio/transforms/_transforms.py:604-616):
+    ``torch.hann_window(n_fft)``, periodic, built by ATen in float32."""
+    return torch.hann_window(n_fft, dtype=torch.float32)
+
+
+def mel_filterbank(n_fft: int, sample_rate: int, n_mels: int) -> torch.Tensor:
+    """(n_fft//2+1, n_mels) float32 HTK triangular filterbank, f_min 0, f_max sr//2, norm None — the table
+    ``melscale_fbanks`` builds for MelSpectrogram's defaults (torchaudio/functional/functional.py:492-587,
+    restated with the same float32 torch ops so the weights are bit-identical; tests compare with the
+    table dumped from torchaudio)."""
+    n_freqs = n_fft // 2 + 1
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + 0.0 / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + float(sample_rate // 2) / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up)).contiguous()
+
+
+class FeaturePlan:
+    """Owns one ``seld_plan`` (constant tables on one device).  Replaces the MelSpectrogram object the
+    reference rebuilds on every call (dataset.py:38-43)."""
+
+    def __init__(self, n_fft: int, hop: int, n_mels: int, sample_rate: int, device: torch.device):
+        self.n_fft, self.hop, self.n_mels, self.sample_rate = int(n_fft), int(hop), int(n_mels), int(sample_rate)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SeldError("seld_cuda has no CPU path: a CUDA device is required")
+        self.window = hann_window(self.n_fft)
+        self.fb = mel_filterbank(self.n_fft, self.sample_rate, self.n_mels)
+        handle = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(_lib.lib().seld_plan_create(ctypes.byref(handle), dev_index, self.n_fft, self.hop, self.n_mels,
+                                               self.window.data_ptr(), self.fb.data_ptr()), "seld_plan_create")
+        self._handle = handle
+        self.device = torch.device("cuda", dev_index)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                _lib.lib().seld_plan_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def num_frames(self, n_samples: int) -> int:
+        return 1 + n_samples // self.hop
+
+    def out_channels(self, mode: int, C: int) -> int:
+        return {SELD_MODE_LOGMEL: C, SELD_MODE_LOGMEL_IV: 7, SELD_MODE_LOGMEL_GCC: 10}[mode]
+
+    def run(self, audio: torch.Tensor, mode="logmel", lengths: torch.Tensor | None = None, out: torch.Tensor | None = None,
+            c_off: int = 0, stats: torch.Tensor | None = None, stat_frames: torch.Tensor | None = None,
+            spec: torch.Tensor | None = None, T_out: int | None = None) -> torch.Tensor:
+        """audio (B, C, N) float32 CUDA (any strides with unit sample stride) -> (B, T_out, C_out, n_mels)."""
+        mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        if audio.dim() != 3:
+            raise ValueError("audio must be (B, C, N)")
+        if audio.dtype != torch.float32 or not audio.is_cuda:
+            raise ValueError("audio must be a float32 CUDA tensor")
+        if audio.device != self.device:
+            raise ValueError(f"audio on {audio.device}, plan on {self.device}")
+        if audio.stride(2) != 1:
+            audio = audio.contiguous()
+        B, Cn, N = audio.shape
+        if T_out is None:
+            T_out = self.num_frames(N)
+        n_out = self.out_channels(mode, Cn)
+        if out is None:
+            out = torch.empty((B, T_out, c_off + n_out, self.n_mels), dtype=torch.float32, device=self.device)
+        if (out.dtype != torch.float32 or not out.is_contiguous() or out.dim() != 4 or out.shape[0] != B
+                or out.shape[1] != T_out or out.shape[3] != self.n_mels or out.device != self.device):
+            raise ValueError("out must be a contiguous float32 (B, T_out, C_out, n_mels) tensor on the plan's device")
+        for name, t, dt in (("lengths", lengths, torch.int64), ("stats", stats, torch.float64),
+                            ("stat_frames", stat_frames, torch.int32), ("spec", spec, torch.complex64)):
+            if t is not None and (t.dtype != dt or not t.is_contiguous() or t.device != self.device):
+                raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
+        if stats is not None and stats.numel() != 2 * out.shape[2] * self.n_mels:
+            raise ValueError("stats must hold 2 * C_out * n_mels float64 values")
+        if spec is not None and tuple(spec.shape) != (B, Cn, T_out, self.n_fft // 2 + 1):
+            raise ValueError("spec must be (B, C, T_out, n_fft//2+1) complex64")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().seld_features(
+                self._handle, mode, audio.data_ptr(), audio.stride(0), audio.stride(1), N, _lib.ptr(lengths), B, Cn,
+                out.data_ptr(), T_out, out.shape[2], c_off, _lib.ptr(stats), _lib.ptr(stat_frames), _lib.ptr(spec),
+                stream), "seld_features")
+        return out
+
+
+_plans: dict = {}
+_plans_lock = threading.Lock()
+
+
+def get_plan(n_fft: int, hop: int, n_mels: int, sample_rate: int, device=None) -> FeaturePlan:
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (int(n_fft), int(hop), int(n_mels), int(sample_rate), str(device))
+    with _plans_lock:
+        p = _plans.get(key)
+        if p is None:
+            p = _plans[key] = FeaturePlan(n_fft, hop, n_mels, sample_rate, device)
+    return p
+
+
+def extract_features(audio: torch.Tensor, sample_rate: int = 24000, n_fft: int = 1024, hop_length: int = 480,
+                     n_mels: int = 64, mode: str = "logmel", **kw) -> torch.Tensor:
+    """Batch API: (B, C, N) float32 CUDA -> (B, T, C_out, n_mels) frame-major features."""
+    return get_plan(n_fft, hop_length, n_mels, sample_rate, audio.device).run(audio, mode=mode, **kw)
+
+
+def _default(name):
+    from .config import get_config
+    return getattr(get_config(), name)
+
+
+def audio_to_mel_spectrogram(waveform: torch.Tensor, sample_rate: int, n_fft=None, hop_length=None, n_mels=None,
+                             device=None) -> torch.Tensor:
+    """Drop-in for reference dataset.py:27-58: (C, N) waveform -> (C, n_mels, 1 + N//hop) float32 dB.
+
+    ``None`` arguments fall back to the Config values like the reference (dataset.py:30-35).  A CPU waveform
+    is copied to the GPU, transformed there and the result returned as a contiguous CPU tensor (what
+    unmodified main.py / DataLoader workers need); a CUDA waveform returns a CUDA tensor that is a
+    (C, n_mels, T) view of the kernel's frame-major output."""
+    if n_fft is None:
+        n_fft = _default("SPECTROGRAM_N_FFT")
+    if hop_length is None:
+        hop_length = _default("SPECTROGRAM_HOP_LENGTH")
+    if n_mels is None:
+        n_mels = _default("N_MELS")
+    if waveform.dim() != 2:
+        raise ValueError("waveform must be (channels, samples)")
+    was_cpu = not waveform.is_cuda
+    dev = torch.device(device) if device is not None else (waveform.device if waveform.is_cuda else torch.device("cuda"))
+    x = waveform.to(device=dev, dtype=torch.float32, non_blocking=True)
+    plan = get_plan(n_fft, hop_length, n_mels, sample_rate, x.device)
+    out = plan.run(x.unsqueeze(0), mode="logmel")[0]  # (T, C, M)
+    res = out.permute(1, 2, 0)
+    return res.contiguous().cpu() if was_cpu else res
+
+
+def extract_features_host(audio_host: torch.Tensor, out_host: torch.Tensor, plan: FeaturePlan, mode="logmel",
+                          chunk: int = 16, n_streams: int = 3) -> torch.Tensor:
+    """End-to-end path for HOST buffers: (B, C, N) float32 (ideally pinned) -> out_host (B, T, C_out, n_mels).
+
+    Clips are streamed through the GPU in chunks on ``n_streams`` CUDA streams so that the host->device
+    copy of chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap (PCIe is full
+    duplex).  Returns when the features are in ``out_host``."""
+    if audio_host.is_cuda or out_host.is_cuda:
+        raise ValueError("extract_features_host takes host tensors; use FeaturePlan.run for device tensors")
+    B, Cn, N = audio_host.shape
+    T = plan.num_frames(N)
+    m = MODES[mode] if isinstance(mode, str) else int(mode)
+    n_out = plan.out_channels(m, Cn)
+    if tuple(out_host.shape) != (B, T, n_out, plan.n_mels) or out_host.dtype != torch.float32:
+        raise ValueError(f"out_host must be float32 {(B, T, n_out, plan.n_mels)}")
+    key = (chunk, Cn, N, n_out, n_streams)
+    cache = plan.__dict__.setdefault("_host_pipes", {})
+    pipe = cache.get(key)
+    if pipe is None:
+        pipe = cache[key] = [(torch.cuda.Stream(plan.device),
+                              torch.empty((chunk, Cn, N), dtype=torch.float32, device=plan.device),
+                              torch.empty((chunk, T, n_out, plan.n_mels), dtype=torch.float32, device=plan.device))
+                             for _ in range(n_streams)]
+    cur = torch.cuda.current_stream(plan.device)
+    for s, _, _ in pipe:
+        s.wait_stream(cur)
+    for i, b0 in enumerate(range(0, B, chunk)):
+        s, d_in, d_out = pipe[i % n_streams]
+        nb = min(chunk, B - b0)
+        with torch.cuda.stream(s):
+            d_in[:nb].copy_(audio_host[b0:b0 + nb], non_blocking=True)
+            plan.run(d_in[:nb], mode=m, out=d_out[:nb])
+            out_host[b0:b0 + nb].copy_(d_out[:nb], non_blocking=True)
+    for s, _, _ in pipe:
+        s.synchronize()
+    return out_host
