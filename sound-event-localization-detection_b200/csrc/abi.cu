@@ -109,7 +109,8 @@ int seld_plan_create(seld_plan** out, int device, int n_fft, int hop, int n_mels
     p->dev.twiddle = reinterpret_cast<const float2*>(d + off_tw);
     p->dev.mel_entries = reinterpret_cast<const int2*>(d + off_mel);
     p->dev.mel_idx = reinterpret_cast<const int*>(d + off_idx);
-    p->feat_smem = total + (size_t)kFeatWarps * 2 * n_bins * sizeof(float4);
+    // per warp: Q rows + max(R rows, 32x33 float2 transpose tile)
+    p->feat_smem = total + (size_t)kFeatWarps * (n_bins + std::max(n_bins, 528)) * sizeof(float4);
     *out = p;
     return SELD_OK;
 }
@@ -151,6 +152,7 @@ int seld_features(seld_plan* plan, int mode, const float* d_audio, int64_t clip_
     a.T_out = T_out;
     a.C_out = C_out;
     a.c_off = c_off;
+    a.n_out = n_out;
     a.stats = d_stats;
     a.stat_frames = d_stat_frames;
     a.spec = reinterpret_cast<float2*>(d_spec);

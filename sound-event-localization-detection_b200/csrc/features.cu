@@ -1,83 +1,92 @@
 // K1+K2 fused: framing + Hann + real FFT (two channels per complex FFT) + power + FOA intensity vectors +
-// sparse mel projection + 10*log10, one warp per (clip, frame), persistent CTAs.
+// sparse mel projection + 10*log10, one warp per (clip, frame), persistent CTAs (one per SM).
 // Replaces reference dataset.py:27-58 (audio_to_mel_spectrogram); IV per SURVEY.md §8(a) A7.
 //
-// Per-warp shared memory: two float4 arrays indexed by bin,
+// Per-warp shared memory (16 656 B): two float4 arrays indexed by bin,
 //   Q[k] = (P0, P1, I1/E, I2/E)   (between the two FFTs: stash of the spectra X0, X1)
-//   R[k] = (P2, P3, I3/E, 0)      (aliased with the 32x32 transpose tile while an FFT is in flight)
+//   R[k] = (P2, P3, I3/E, 0)      (aliased with the 32x33 transpose tile while an FFT is in flight)
 // so the mel gather reads two LDS.128 per filterbank non-zero for all 7 feature channels.
+//
+// Latency hiding with only 12 warps per SM (shared memory bound) is done by register prefetch: the raw
+// samples of channel pair b are requested before the post-processing of pair a, and the samples of the NEXT
+// frame's pair a before the mel gather of the current frame, when the FFT registers are dead.
 #include "seld_common.h"
 #include "warp_fft.cuh"
 
 namespace seld {
 
-__device__ __forceinline__ float ldg_or_zero(const float* p, long long i) { return p ? __ldg(p + i) : 0.f; }
-
 template <int R1>
-__device__ __forceinline__ void load_pair(float2 (&v)[R1], const float* xa, const float* xb, long long start,
-                                          long long len, const float* s_win, int lane) {
+__device__ __forceinline__ void load_raw(float2 (&v)[R1], const float* xa, const float* xb, long long start,
+                                         long long len, int lane) {
     using F = WarpFft<R1>;
     const bool interior = (start >= 0) && (start + F::N <= len);
     if (interior) {
-        const float* pa = xa ? xa + start + lane : nullptr;
-        const float* pb = xb ? xb + start + lane : nullptr;
+        const float* pa = xa + start + lane;
+        if (xb) {
+            const float* pb = xb + start + lane;
 #pragma unroll
-        for (int j = 0; j < R1; ++j) {
-            float w = s_win[lane + 32 * j];
-            float a = pa ? __ldg(pa + 32 * j) : 0.f;
-            float b = pb ? __ldg(pb + 32 * j) : 0.f;
-            v[j] = make_float2(a * w, b * w);
+            for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(pa + 32 * j), __ldg(pb + 32 * j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(pa + 32 * j), 0.f);
         }
     } else {
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
-            long long idx = F::reflect(start + lane + 32 * j, len);
-            float w = s_win[lane + 32 * j];
-            v[j] = make_float2(ldg_or_zero(xa, idx) * w, ldg_or_zero(xb, idx) * w);
+            const long long idx = F::reflect(start + lane + 32 * j, len);
+            v[j] = make_float2(__ldg(xa + idx), xb ? __ldg(xb + idx) : 0.f);
         }
     }
 }
 
-// Full complex FFT of one channel pair; result in u (lane = k_lo, register = k_hi).
+// window -> pass 1 -> transpose -> pass 2; result in u (lane = k_lo, register = k_hi)
 template <int R1>
-__device__ __forceinline__ void fft_pair(float2 (&u)[32], const float* xa, const float* xb, long long start,
-                                         long long len, const float* s_win, const float2* s_tw, float2* T, int lane) {
+__device__ __forceinline__ void fft_from_raw(float2 (&u)[32], float2 (&v)[R1], const float* s_win, const float2* s_tw,
+                                             float2* T, int lane) {
     using F = WarpFft<R1>;
-    {
-        float2 v[R1];
-        load_pair<R1>(v, xa, xb, start, len, s_win, lane);
-        F::pass1(v, s_tw + lane);
-        __syncwarp();  // everyone is done reading whatever lived in T / R before
-        F::t_store(v, T, lane);
+#pragma unroll
+    for (int j = 0; j < R1; ++j) {
+        const float w = s_win[lane + 32 * j];
+        v[j].x *= w;
+        v[j].y *= w;
     }
+    F::pass1(v, s_tw + lane);
+    __syncwarp();  // every lane is done reading whatever lived in T / R before
+    F::t_store(v, T, lane);
     __syncwarp();
     F::t_load(u, T, lane);
     __syncwarp();  // T may be overwritten (R rows / next transpose) once all lanes have loaded
     F::pass2(u);
 }
 
-template <int NCH>
-__device__ __forceinline__ void flush_stats(double* stats, int CM, int chan0, int nch, int n_mels, int melA, int melB,
-                                            float* st_sum, float* st_sq) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int m = s ? melB : melA;
-        if (m < 0) continue;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            if (c < 4 && c >= nch) continue;
-            const int f = (chan0 + c) * n_mels + m;
-            atomicAdd(stats + f, (double)st_sum[s * NCH + c]);
-            atomicAdd(stats + CM + f, (double)st_sq[s * NCH + c]);
-            st_sum[s * NCH + c] = st_sq[s * NCH + c] = 0.f;
-        }
-    }
+// mirror-bin exchange + channel split for register k_hi (0..15) of every lane
+template <int R1, int KH>
+__device__ __forceinline__ void split_pair(const float2 (&u)[32], int lane, int src, float2& xa, float2& xb) {
+    const float2 z = u[KH], m = u[31 - KH];
+    float2 p;
+    p.x = __shfl_sync(0xffffffffu, m.x, src);
+    p.y = __shfl_sync(0xffffffffu, m.y, src);
+    const float2 own = u[(32 - KH) & 31];  // lane 0 holds its own mirror bins
+    p.x = lane == 0 ? own.x : p.x;
+    p.y = lane == 0 ? own.y : p.y;
+    WarpFft<R1>::unpack(z, p, xa, xb);
 }
 
-template <int R1, bool IV, bool STATS>
+struct ItemCtx {
+    const float* x;     // channel c0 of the clip
+    float* out_row;     // out[b, t, c_off + c0, 0]
+    float2* spec;       // spec[b, c0, t, 0] or null
+    long long start, len;
+    int nch;
+    bool valid;         // t < T_b (padding rows of a ragged batch are written as 0)
+};
+
+template <int R1, bool IV, bool SPEC>
 __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p, FeatArgs a) {
     using F = WarpFft<R1>;
     constexpr int N = F::N, NB = F::NB;
+    constexpr int NCH = IV ? 7 : 4;
+    constexpr int WARP_F4 = NB + (F::T_FLOAT2 > 2 * NB ? (F::T_FLOAT2 + 1) / 2 : NB);  // Q rows + max(R rows, T tile)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(s_win + N);
@@ -93,183 +102,231 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float4* Q = s_qr + warp * (2 * NB);
+    float4* Q = s_qr + warp * WARP_F4;
     float4* R = Q + NB;
     float2* T = reinterpret_cast<float2*>(R);
+    const unsigned char* Qb = reinterpret_cast<const unsigned char*>(Q);
     const int src = F::partner_lane(lane);
-    const unsigned full = 0xffffffffu;
     const int melA = s_midx[lane], melB = s_midx[32 + lane];
     const int n_mels = p.n_mels;
-    constexpr int NCH = IV ? 7 : 4;
+    const bool active = lane < R1;  // lanes >= R1 (n_fft 960) own no bins
 
-    float st_sum[STATS ? 2 * NCH : 1], st_sq[STATS ? 2 * NCH : 1];
-    if (STATS) {
-#pragma unroll
-        for (int i = 0; i < 2 * NCH; ++i) st_sum[i] = st_sq[i] = 0.f;
-    }
-    int st_group = -1;  // stats registers belong to one channel group at a time
-
-    // n_items < 2^31 (checked on the host): 32-bit index arithmetic
+    // ---- work distribution: item = (b*G + g)*T_out + t, items of one warp are warps_total apart ----
     const unsigned warps_total = gridDim.x * kFeatWarps;
-    const unsigned n_items = (unsigned)a.n_items, T_out32 = (unsigned)a.T_out;
-    for (unsigned item = blockIdx.x * kFeatWarps + warp; item < n_items; item += warps_total) {
-        const unsigned bg = item / T_out32;
-        const long long t = item - bg * T_out32;
-        const int g = int(bg % (unsigned)a.G);
-        const long long b = bg / (unsigned)a.G;
-        const long long len = a.lengths ? a.lengths[b] : a.n_samples;
-        const long long T_b = 1 + len / p.hop;
-        const int c0 = 4 * g;
-        const int nch = min(4, a.C - c0);
-        float* out_row = a.out + ((b * a.T_out + t) * a.C_out + a.c_off + c0) * n_mels;
+    const unsigned n_items = (unsigned)a.n_items, T_out = (unsigned)a.T_out;
+    unsigned item = blockIdx.x * kFeatWarps + warp;
+    if (item >= n_items) return;
+    unsigned bg = item / T_out, t = item - bg * T_out;
+    long long len_cache_b = -1, len_cache = a.n_samples;
 
-        if (t >= T_b) {  // padding rows of a ragged batch
-            const int n_out = IV ? 7 : nch;
-            for (int c = 0; c < n_out; ++c) {
-                if (melA >= 0) out_row[c * n_mels + melA] = 0.f;
-                if (melB >= 0) out_row[c * n_mels + melB] = 0.f;
-            }
-            continue;
+    auto make_ctx = [&](unsigned bg_, unsigned t_) {
+        ItemCtx c;
+        const unsigned g = a.G == 1 ? 0u : bg_ % (unsigned)a.G;
+        const long long b = a.G == 1 ? (long long)bg_ : (long long)(bg_ / (unsigned)a.G);
+        if (a.lengths && b != len_cache_b) {
+            len_cache = a.lengths[b];
+            len_cache_b = b;
         }
+        c.len = len_cache;
+        const int c0 = 4 * (int)g;
+        c.nch = min(4, a.C - c0);
+        c.valid = (long long)t_ < 1 + c.len / p.hop;
+        c.start = c.valid ? (long long)t_ * p.hop - F::HALF : 0;  // padding rows read frame 0 and are zeroed at the store
+        c.x = a.audio + b * a.clip_stride + (long long)c0 * a.chan_stride;
+        c.out_row = a.out + ((b * a.T_out + t_) * a.C_out + a.c_off + c0) * n_mels;
+        c.spec = SPEC ? a.spec + ((b * a.C + c0) * a.T_out + t_) * NB : nullptr;
+        return c;
+    };
 
-        const float* x = a.audio + b * a.clip_stride + (long long)c0 * a.chan_stride;
-        const long long start = t * p.hop - F::HALF;
-        float2* spec = a.spec ? a.spec + ((b * a.C + c0) * a.T_out + t) * NB : nullptr;
-        const long long spec_cs = a.T_out * NB;  // channel stride of the spectrum dump
+    ItemCtx cur = make_ctx(bg, t);
+    float2 v[R1];
+    load_raw<R1>(v, cur.x, cur.nch > 1 ? cur.x + a.chan_stride : nullptr, cur.start, cur.len, lane);
 
+    while (true) {
         float2 u[32];
-        // ---- channel pair (c0, c0+1) ----
-        fft_pair<R1>(u, x, nch > 1 ? x + a.chan_stride : nullptr, start, len, s_win, s_tw, T, lane);
-#pragma unroll
-        for (int kh = 0; kh <= 16; ++kh) {
-            if (kh == 16 && lane != 0) break;  // Nyquist bin lives in lane 0 only
-            float2 z = u[kh], m = u[31 - (kh & 15)], pz;
-            if (kh < 16) {
-                pz.x = __shfl_sync(full, m.x, src);
-                pz.y = __shfl_sync(full, m.y, src);
-                if (lane == 0) pz = u[(32 - kh) & 31];
-            } else {
-                pz = z;
-            }
+        const long long spec_cs = a.T_out * NB;  // channel stride of the spectrum dump
+        // ================= channel pair (c0, c0+1) =================
+        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane);
+        const bool have_b = cur.nch > 2;
+        if (have_b)  // request pair b now; it lands while pair a is post-processed
+            load_raw<R1>(v, cur.x + 2 * a.chan_stride, cur.nch > 3 ? cur.x + 3 * a.chan_stride : nullptr, cur.start,
+                         cur.len, lane);
+        static_for<16>([&](auto KH) {
+            constexpr int kh = decltype(KH)::value;
             float2 x0, x1;
-            F::unpack(z, pz, x0, x1);
-            const int k = F::bin_of(lane, kh);
-            if (lane < R1) {
+            split_pair<R1, kh>(u, lane, src, x0, x1);
+            const int k = lane + R1 * kh;
+            if (active) {
                 Q[k] = make_float4(x0.x, x0.y, x1.x, x1.y);
-                if (spec) {
-                    spec[k] = x0;
-                    if (nch > 1) spec[spec_cs + k] = x1;
+                if (SPEC) {
+                    cur.spec[k] = x0;
+                    if (cur.nch > 1) cur.spec[spec_cs + k] = x1;
                 }
+            }
+        });
+        if (lane == 0) {  // Nyquist bin: its own mirror
+            float2 x0, x1;
+            F::unpack(u[16], u[16], x0, x1);
+            Q[NB - 1] = make_float4(x0.x, x0.y, x1.x, x1.y);
+            if (SPEC) {
+                cur.spec[NB - 1] = x0;
+                if (cur.nch > 1) cur.spec[spec_cs + NB - 1] = x1;
             }
         }
-        // ---- channel pair (c0+2, c0+3) ----
-        const bool have_b = nch > 2;
-        if (have_b)
-            fft_pair<R1>(u, x + 2 * a.chan_stride, nch > 3 ? x + 3 * a.chan_stride : nullptr, start, len, s_win,
-                         s_tw, T, lane);
-        else
-            __syncwarp();
+        // ================= channel pair (c0+2, c0+3) =================
+        if (have_b) {
+            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane);
+        } else {
 #pragma unroll
-        for (int kh = 0; kh <= 16; ++kh) {
-            if (kh == 16 && lane != 0) break;
-            float2 x2 = make_float2(0.f, 0.f), x3 = x2;
-            if (have_b) {
-                float2 z = u[kh], m = u[31 - (kh & 15)], pz;
-                if (kh < 16) {
-                    pz.x = __shfl_sync(full, m.x, src);
-                    pz.y = __shfl_sync(full, m.y, src);
-                    if (lane == 0) pz = u[(32 - kh) & 31];
-                } else {
-                    pz = z;
-                }
-                F::unpack(z, pz, x2, x3);
-            }
-            const int k = F::bin_of(lane, kh);
-            if (lane < R1) {
-                float4 s = Q[k];
+            for (int i = 0; i < 32; ++i) u[i] = make_float2(0.f, 0.f);
+            __syncwarp();
+        }
+        static_for<16>([&](auto KH) {
+            constexpr int kh = decltype(KH)::value;
+            float2 x2, x3;
+            split_pair<R1, kh>(u, lane, src, x2, x3);
+            const int k = lane + R1 * kh;
+            if (active) {
+                const float4 s = Q[k];
                 float4 q, r;
                 bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
                 Q[k] = q;
                 R[k] = r;
-                if (spec && have_b) {
-                    spec[2 * spec_cs + k] = x2;
-                    if (nch > 3) spec[3 * spec_cs + k] = x3;
+                if (SPEC && have_b) {
+                    cur.spec[2 * spec_cs + k] = x2;
+                    if (cur.nch > 3) cur.spec[3 * spec_cs + k] = x3;
                 }
             }
+        });
+        if (lane == 0) {
+            float2 x2, x3;
+            F::unpack(u[16], u[16], x2, x3);
+            const float4 s = Q[NB - 1];
+            float4 q, r;
+            bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
+            Q[NB - 1] = q;
+            R[NB - 1] = r;
+            if (SPEC && have_b) {
+                cur.spec[2 * spec_cs + NB - 1] = x2;
+                if (cur.nch > 3) cur.spec[3 * spec_cs + NB - 1] = x3;
+            }
         }
-        __syncwarp();
 
-        // ---- sparse mel projection: slot A then slot B of this lane ----
+        // ================= next item: request its pair a while the mel gather runs =================
+        t += warps_total;
+        while (t >= T_out) {
+            t -= T_out;
+            ++bg;
+        }
+        item += warps_total;
+        const bool more = item < n_items;
+        const ItemCtx done = cur;
+        if (more) {
+            cur = make_ctx(bg, t);
+            load_raw<R1>(v, cur.x, cur.nch > 1 ? cur.x + a.chan_stride : nullptr, cur.start, cur.len, lane);
+        }
+        __syncwarp();  // Q / R rows of all lanes are visible
+
+        // ================= sparse mel projection: slot A then slot B of this lane =================
         float acc[2][NCH];
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
             for (int c = 0; c < NCH; ++c) acc[s][c] = 0.f;
         const int2* e = s_mel + lane;
-#pragma unroll 4
-        for (int i = 0; i < p.la; ++i, e += 32) {
-            const int2 en = *e;
-            const float w = __int_as_float(en.y);
-            const float4 q = Q[en.x], r = R[en.x];
-            acc[0][0] = fmaf(w, q.x, acc[0][0]);
-            acc[0][1] = fmaf(w, q.y, acc[0][1]);
-            acc[0][2] = fmaf(w, r.x, acc[0][2]);
-            acc[0][3] = fmaf(w, r.y, acc[0][3]);
-            if (IV) {
-                acc[0][4] = fmaf(w, q.z, acc[0][4]);
-                acc[0][5] = fmaf(w, q.w, acc[0][5]);
-                acc[0][6] = fmaf(w, r.z, acc[0][6]);
-            }
-        }
-#pragma unroll 4
-        for (int i = 0; i < p.lb; ++i, e += 32) {
-            const int2 en = *e;
-            const float w = __int_as_float(en.y);
-            const float4 q = Q[en.x], r = R[en.x];
-            acc[1][0] = fmaf(w, q.x, acc[1][0]);
-            acc[1][1] = fmaf(w, q.y, acc[1][1]);
-            acc[1][2] = fmaf(w, r.x, acc[1][2]);
-            acc[1][3] = fmaf(w, r.y, acc[1][3]);
-            if (IV) {
-                acc[1][4] = fmaf(w, q.z, acc[1][4]);
-                acc[1][5] = fmaf(w, q.w, acc[1][5]);
-                acc[1][6] = fmaf(w, r.z, acc[1][6]);
-            }
-        }
-
-        // ---- log + store: out[b, t, c_off + c0 + c, m] ----
-        if (STATS && st_group != g) {  // only when C > 4: partial sums belong to one channel group at a time
-            if (st_group >= 0)
-                flush_stats<NCH>(a.stats, a.C_out * n_mels, a.c_off + 4 * st_group, min(4, a.C - 4 * st_group), n_mels,
-                                 melA, melB, st_sum, st_sq);
-            st_group = g;
-        }
-        const bool in_stats = STATS && (t < (a.stat_frames ? (long long)a.stat_frames[b] : T_b));
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            const int m = s ? melB : melA;
-            if (m < 0) continue;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                if (c < 4 && c >= nch) continue;
-                const float v = c < 4 ? power_to_db(acc[s][c]) : acc[s][c];
-                out_row[c * n_mels + m] = v;
-                if (STATS && in_stats) {
-                    st_sum[s * NCH + c] += v;
-                    st_sq[s * NCH + c] = fmaf(v, v, st_sq[s * NCH + c]);
+            const int n_it = s ? p.lb : p.la;  // multiples of 4 (host pads)
+#pragma unroll 4
+            for (int i = 0; i < n_it; ++i, e += 32) {
+                const int2 en = *e;  // {byte offset of the bin row, weight bits}
+                const float w = __int_as_float(en.y);
+                const float4 q = *reinterpret_cast<const float4*>(Qb + en.x);
+                const float4 r = *reinterpret_cast<const float4*>(Qb + en.x + NB * 16);
+                acc[s][0] = fmaf(w, q.x, acc[s][0]);
+                acc[s][1] = fmaf(w, q.y, acc[s][1]);
+                acc[s][2] = fmaf(w, r.x, acc[s][2]);
+                acc[s][3] = fmaf(w, r.y, acc[s][3]);
+                if (IV) {
+                    acc[s][4] = fmaf(w, q.z, acc[s][4]);
+                    acc[s][5] = fmaf(w, q.w, acc[s][5]);
+                    acc[s][6] = fmaf(w, r.z, acc[s][6]);
                 }
             }
         }
-    }
 
-    if (STATS && st_group >= 0)
-        flush_stats<NCH>(a.stats, a.C_out * n_mels, a.c_off + 4 * st_group, min(4, a.C - 4 * st_group), n_mels, melA,
-                         melB, st_sum, st_sq);
+        // ================= log + store: out[b, t, c_off + c0 + c, m] =================
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int m = s ? melB : melA;
+            if (m >= 0) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (c < 4 && c >= done.nch) continue;
+                    const float val = c < 4 ? power_to_db(acc[s][c]) : acc[s][c];
+                    done.out_row[c * n_mels + m] = done.valid ? val : 0.f;
+                }
+            }
+        }
+        if (!more) break;
+    }
 }
 
-template <int R1, bool IV, bool STATS>
+// ---- scaler partials: per-feature sum and sum of squares over the kept frames ----
+// x (B, T_out, F) float32; for the columns [col0, col0 + ncols): stats[f] += sum, stats[F + f] += sum of
+// squares over rows t < frames[b] (or t < 1 + len_b/hop when frames is null).
+// CTA = 64 columns x 8 row lanes over a slab of kStatRows rows: every warp reads 128 contiguous bytes per
+// row, 4 rows in flight per thread; float partials over <= 32 rows, then double across row lanes and CTAs.
+constexpr int kStatRows = 256;
+__global__ void __launch_bounds__(512) feature_stats_kernel(const float* __restrict__ x, long long T_out, int F,
+                                                            int col0, int ncols, int B, const int* __restrict__ frames,
+                                                            const long long* __restrict__ lengths, long long n_samples,
+                                                            int hop, double* __restrict__ stats) {
+    __shared__ unsigned char s_valid[kStatRows];
+    __shared__ double s_sum[8][64], s_sq[8][64];
+    const long long total_rows = (long long)B * T_out;
+    const long long r0 = (long long)blockIdx.x * kStatRows;
+    const int n_rows = (int)min((long long)kStatRows, total_rows - r0);
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    if (tid < kStatRows) {
+        bool ok = false;
+        if (tid < n_rows) {
+            const long long r = r0 + tid, b = r / T_out, t = r - b * T_out;
+            const long long lim = frames ? (long long)frames[b] : 1 + (lengths ? lengths[b] : n_samples) / hop;
+            ok = t < lim;
+        }
+        s_valid[tid] = ok;
+    }
+    __syncthreads();
+    const int j = blockIdx.y * 64 + threadIdx.x;
+    float cs = 0.f, css = 0.f;
+    if (j < ncols) {
+        const float* px = x + r0 * F + col0 + j;
+#pragma unroll 4
+        for (int r = threadIdx.y; r < n_rows; r += 8) {
+            const float v = s_valid[r] ? __ldg(px + (long long)r * F) : 0.f;
+            cs += v;
+            css = fmaf(v, v, css);
+        }
+    }
+    s_sum[threadIdx.y][threadIdx.x] = (double)cs;
+    s_sq[threadIdx.y][threadIdx.x] = (double)css;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < ncols) {
+        double s = 0.0, ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s += s_sum[i][threadIdx.x];
+            ss += s_sq[i][threadIdx.x];
+        }
+        atomicAdd(stats + col0 + j, s);
+        atomicAdd(stats + F + col0 + j, ss);
+    }
+}
+
+template <int R1, bool IV, bool SPEC>
 static int launch_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    auto kern = features_kernel<R1, IV, STATS>;
+    auto kern = features_kernel<R1, IV, SPEC>;
     SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->feat_smem));
     long long ctas = (a.n_items + kFeatWarps - 1) / kFeatWarps;
     if (ctas > plan->num_sms) ctas = plan->num_sms;
@@ -279,14 +336,31 @@ static int launch_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t str
     return SELD_OK;
 }
 
+int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
+    const int F = a.C_out * plan->dev.n_mels;
+    const long long rows = (long long)a.B * a.T_out;
+    const int ncols = a.n_out * plan->dev.n_mels;
+    if (rows < 1 || ncols < 1) return SELD_OK;
+    dim3 grid((unsigned)((rows + kStatRows - 1) / kStatRows), (unsigned)((ncols + 63) / 64)), block(64, 8);
+    feature_stats_kernel<<<grid, block, 0, stream>>>(a.out, a.T_out, F, a.c_off * plan->dev.n_mels, ncols, a.B,
+                                                     a.stat_frames, a.lengths, a.n_samples, plan->dev.hop, a.stats);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
 int launch_features(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream) {
-    const bool st = a.stats != nullptr;
+    const bool sp = a.spec != nullptr;
+    int rc;
     if (plan->dev.r1 == 32) {
-        if (iv) return st ? launch_one<32, true, true>(plan, a, stream) : launch_one<32, true, false>(plan, a, stream);
-        return st ? launch_one<32, false, true>(plan, a, stream) : launch_one<32, false, false>(plan, a, stream);
+        if (iv) rc = sp ? launch_one<32, true, true>(plan, a, stream) : launch_one<32, true, false>(plan, a, stream);
+        else rc = sp ? launch_one<32, false, true>(plan, a, stream) : launch_one<32, false, false>(plan, a, stream);
+    } else {
+        if (iv) rc = sp ? launch_one<30, true, true>(plan, a, stream) : launch_one<30, true, false>(plan, a, stream);
+        else rc = sp ? launch_one<30, false, true>(plan, a, stream) : launch_one<30, false, false>(plan, a, stream);
     }
-    if (iv) return st ? launch_one<30, true, true>(plan, a, stream) : launch_one<30, true, false>(plan, a, stream);
-    return st ? launch_one<30, false, true>(plan, a, stream) : launch_one<30, false, false>(plan, a, stream);
+    if (rc != SELD_OK) return rc;
+    if (a.stats) return launch_feature_stats(plan, a, stream);
+    return SELD_OK;
 }
 
 }  // namespace seld

@@ -18,7 +18,7 @@ namespace seld {
 // a lane has spare iterations and no conflict-free row left.
 struct MelTables {
     int la = 0, lb = 0;
-    std::vector<int2> entries;  // [(la+lb)][32]
+    std::vector<int2> entries;  // [(la+lb)][32]: {byte offset of bin row, weight bits}
     std::vector<int> idx;       // [2][32]
 };
 
@@ -71,7 +71,7 @@ inline void schedule_slot(const std::vector<std::vector<std::pair<int, float>>>&
             }
             for (int l = 0; l < 8; ++l) {
                 int2 e;
-                e.x = chosen_row[l];
+                e.x = chosen_row[l] * 16;  // byte offset of the float4 row
                 std::memcpy(&e.y, &chosen_w[l], 4);
                 out[base + (size_t)it * 32 + q * 8 + l] = e;
             }
@@ -95,6 +95,8 @@ inline MelTables build_mel_tables(const float* fb, int n_bins, int n_mels) {
         t.la = std::max(t.la, (int)A[l].size());
         t.lb = std::max(t.lb, (int)Bs[l].size());
     }
+    t.la = (t.la + 3) & ~3;  // the kernel unrolls the gather by 4
+    t.lb = (t.lb + 3) & ~3;
     schedule_slot(A, t.la, t.entries);
     schedule_slot(Bs, t.lb, t.entries);
     return t;

@@ -15,10 +15,10 @@ constexpr int kFeatWarps = 12;  // warps per CTA of the feature kernel (1 CTA / 
 // Device-side view of a plan (passed by value to kernels).
 struct PlanDev {
     int n_fft, r1, hop, n_bins, n_mels;
-    int la, lb;                // trip counts of the two mel gather loops
+    int la, lb;                // trip counts of the two mel gather loops (multiples of 4)
     const float* window;       // [n_fft], pre-scaled by 1/2 (exact) so the channel split needs no factor
     const float2* twiddle;     // [r1][32]: W_N^{lane*k_lo}
-    const int2* mel_entries;   // [la+lb][32]: {.x = bin, .y = float bits of weight}
+    const int2* mel_entries;   // [la+lb][32]: {.x = byte offset of the bin row (bin*16), .y = float bits of weight}
     const int* mel_idx;        // [2][32]: mel index of slot A / slot B per lane, -1 = none
 };
 
@@ -29,7 +29,7 @@ struct FeatArgs {
     int B, C, G;                // G = channel groups of 4
     float* out;
     long long T_out;
-    int C_out, c_off;
+    int C_out, c_off, n_out;     // n_out = channels this call writes
     double* stats;              // may be null
     const int* stat_frames;     // may be null
     float2* spec;               // may be null

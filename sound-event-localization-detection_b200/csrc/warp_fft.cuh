@@ -6,7 +6,7 @@
 // Decomposition (n = lane + 32 j, k = k_lo + R1 k_hi):
 //   pass 1 (registers): Y[lane][k_lo] = sum_j v[j] W_R1^{j k_lo}          (Dft<R1>, immediates)
 //   twiddle           : Y *= W_N^{lane k_lo}                               (table tw[k_lo][lane], smem)
-//   transpose (smem)  : lane <-> k_lo, XOR-swizzled 32x32 float2 tile, conflict-free both ways
+//   transpose (smem)  : lane <-> k_lo, 32x32 float2 tile with row pitch 33, conflict-free both ways
 //   pass 2 (registers): X[k_lo + R1 k_hi] = sum_n u[n] W_32^{n k_hi}       (Dft<32>, immediates)
 // After pass 2 lane k_lo holds bins k_lo + R1*k_hi in register k_hi.  The mirror bin N-k needed to split
 // the two real channels lives in lane (R1 - k_lo) % R1, register 31 - k_hi (32 - k_hi for lane 0), i.e.
@@ -41,22 +41,26 @@ struct WarpFft {
         });
     }
 
-    // transpose through the swizzled tile T (float2[32*32]); element (row k_lo, col lane) at row*32 + (col ^ row)
+    // transpose through the tile T: element (row k_lo, col lane) at row*TP + col, row pitch TP = 33 float2.
+    // Stores (fixed row, consecutive lanes) and loads (fixed column, row = lane: 66*lane words -> bank pair
+    // 2*lane mod 32, distinct over a half-warp) are both conflict-free, and every address is lane base +
+    // compile-time immediate.
+    static constexpr int TP = 33;
+    static constexpr int T_FLOAT2 = 32 * TP;
     static SELD_HD void t_store(const float2 (&v)[R1], float2* T, int lane) {
+        float2* p = T + lane;
         static_for<R1>([&](auto K) {
             constexpr int k = decltype(K)::value;
-            T[k * 32 + (lane ^ k)] = v[k];
+            p[k * TP] = v[k];
         });
     }
     static SELD_HD void t_load(float2 (&u)[32], const float2* T, int lane) {
-        if (R1 < 32 && lane >= R1) {
-            static_for<32>([&](auto C) { u[decltype(C)::value] = make_float2(0.f, 0.f); });
-            return;
-        }
+        const float2* p = T + (R1 < 32 && lane >= R1 ? 0 : lane) * TP;
         static_for<32>([&](auto C) {
             constexpr int c = decltype(C)::value;
-            u[c] = T[lane * 32 + (c ^ lane)];
+            u[c] = p[c];
         });
+        if (R1 < 32 && lane >= R1) static_for<32>([&](auto C) { u[decltype(C)::value] = make_float2(0.f, 0.f); });
     }
     static SELD_HD void pass2(float2 (&u)[32]) { Dft<32, false>::run(u); }
 

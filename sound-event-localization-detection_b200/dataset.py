@@ -1,0 +1,327 @@
+"""Drop-in for the reference's ``dataset.py`` (dataset.py:1-330): ``load_audio``, ``audio_to_mel_spectrogram``,
+``metadata_to_labels``, ``load_files`` and ``SELDDataset`` with the same names, arguments, attributes and log
+lines, plus the Gaussian-label switch of smrl_seld_gaussian.py:540 (``use_gaussian_augmentation``).
+
+B200-first differences (none visible through the reference API):
+  * features and labels of every file are produced by the CUDA kernels and written in place into the two
+    concatenated tensors (no per-file tensors, no torch.cat);
+  * the concatenated features are kept frame-major ``(sum T, C, F)`` — what ``__getitem__`` hands out
+    (dataset.py:303) — ``concatenated_spectrograms`` is the ``(C, F, sum T)`` view of it;
+  * ``resident="cuda"`` keeps everything in HBM (65 GB of labels for a 10 h corpus fit in 180 GB) and
+    ``DeviceLoader`` assembles batches there; ``resident="cpu"`` (default, what unmodified main.py with
+    DataLoader workers + pin_memory needs) copies the two tensors back once;
+  * ``labels="compact"`` keeps only the event tables and paints label windows per batch.
+"""
+from __future__ import annotations
+
+import logging
+from glob import glob
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import _lib, labels as L
+from .audio_io import load_audio  # noqa: F401  (re-exported like the reference's dataset.load_audio)
+from .config import get_config
+from .features import audio_to_mel_spectrogram, get_plan  # noqa: F401
+from .labels import augment_with_gaussian_noise, metadata_to_labels, polar_to_grid  # noqa: F401
+
+logger = logging.getLogger("SMR_SELD")
+
+FEATURE_MODES = {"logmel": "logmel", "foa_iv": "logmel_iv", "logmel_iv": "logmel_iv", "mic_gcc": "logmel_gcc",
+                 "logmel_gcc": "logmel_gcc"}
+
+
+def load_files():
+    """Reference dataset.py:121-165: sorted wav lists of the four dev folders with matching CSVs."""
+    config = get_config()
+    if config.USE_FULL_DATASET:
+        sony_train_audio = sorted(glob(str(config.SONY_TRAIN_DIR / "*.wav")))
+        tau_train_audio = sorted(glob(str(config.TAU_TRAIN_DIR / "*.wav")))
+        sony_test_audio = sorted(glob(str(config.SONY_TEST_DIR / "*.wav")))
+        tau_test_audio = sorted(glob(str(config.TAU_TEST_DIR / "*.wav")))
+
+        def get_matching_metadata(audio_files, meta_dir):
+            meta_files = []
+            for audio_file in audio_files:
+                meta_file = meta_dir / f"{Path(audio_file).stem}.csv"
+                if meta_file.exists():
+                    meta_files.append(str(meta_file))
+                else:
+                    raise FileNotFoundError(f"Metadata file not found: {meta_file}")
+            return meta_files
+
+        train_audio_files = sony_train_audio + tau_train_audio
+        train_meta_files = (get_matching_metadata(sony_train_audio, config.SONY_TRAIN_META_DIR)
+                            + get_matching_metadata(tau_train_audio, config.TAU_TRAIN_META_DIR))
+        test_audio_files = sony_test_audio + tau_test_audio
+        test_meta_files = (get_matching_metadata(sony_test_audio, config.SONY_TEST_META_DIR)
+                           + get_matching_metadata(tau_test_audio, config.TAU_TEST_META_DIR))
+    else:
+        train_audio_files = [str(config.TRAIN_AUDIO_PATH)]
+        train_meta_files = [str(config.TRAIN_META_PATH)]
+        test_audio_files = [str(config.TEST_AUDIO_PATH)]
+        test_meta_files = [str(config.TEST_META_PATH)]
+    return train_audio_files, train_meta_files, test_audio_files, test_meta_files
+
+
+class SELDDataset(Dataset):
+    """Reference dataset.py:167-330 (+ smrl_seld_gaussian.py:539-700 for ``use_gaussian_augmentation``)."""
+
+    def __init__(self, audio_files, metadata_files, num_classes=14, use_gaussian_augmentation=False, *,
+                 device=None, resident="cpu", labels="dense", feature_type=None, audio_loader=None,
+                 compute_stats=False):
+        assert len(audio_files) == len(metadata_files), \
+            "Number of audio files must match number of metadata files"
+        config = get_config()
+        self.audio_files = audio_files
+        self.metadata_files = metadata_files
+        self.sample_rate = config.SR
+        self.n_fft = config.SPECTROGRAM_N_FFT
+        self.spectrogram_hop_length = config.SPECTROGRAM_HOP_LENGTH
+        self.n_mels = config.N_MELS
+        self.cell_size_deg = config.GRID_CELL_DEGREES
+        self.num_classes = num_classes
+        self.use_gaussian_augmentation = use_gaussian_augmentation
+        self.I = int(180 // self.cell_size_deg)
+        self.J = int(360 // self.cell_size_deg)
+        self.total_cells = self.I * self.J
+        self.window_length_samples = config.WINDOW_LENGTH
+        self.hop_length_samples = config.HOP_LENGTH
+        self.window_length_frames = int(self.window_length_samples / self.spectrogram_hop_length)
+        self.hop_length_frames = int(self.hop_length_samples / self.spectrogram_hop_length)
+
+        if resident not in ("cpu", "cuda") or labels not in ("dense", "compact"):
+            raise ValueError("resident must be 'cpu' or 'cuda'; labels must be 'dense' or 'compact'")
+        if labels == "compact" and resident != "cuda":
+            raise ValueError("labels='compact' paints label windows on the GPU: use resident='cuda'")
+        self.resident, self.label_mode = resident, labels
+        self.feature_type = feature_type or getattr(config, "FEATURE_TYPE", "logmel")
+        self._mode = FEATURE_MODES[self.feature_type]
+        self.device = L._cuda_device(device)
+        self._load_audio = audio_loader or load_audio
+        self._compute_stats = compute_stats
+
+        logger.info(f"SELDDataset initialization started...")
+        logger.info(f"  Files: {len(audio_files)} audio files")
+        logger.info(f"  Grid: {self.I}x{self.J} = {self.total_cells} cells")
+        logger.info(f"  Window: {self.window_length_frames} frames ({self.window_length_samples / self.sample_rate:.1f}s)")
+        logger.info(f"  Hop: {self.hop_length_frames} frames ({self.hop_length_samples / self.sample_rate:.1f}s)")
+        logger.info(f"  Label augmentation: {'Gaussian noise' if use_gaussian_augmentation else 'Standard (metadata_to_labels)'}")
+
+        self._load_and_concatenate_all()
+        self._create_windows()
+        logger.info(f"SELDDataset initialized with {len(self.windows)} windows")
+
+    # ------------------------------------------------------------------------------------------
+    def _load_and_concatenate_all(self):
+        """dataset.py:212-265, restructured: pass 1 reads audio + metadata on the host (sizes, events), then the
+        GPU writes every file's features and labels straight into the concatenated tensors."""
+        logger.info("Loading and processing all audio files...")
+        waves, per_file = [], []
+        total = 0
+        for idx, (audio_path, metadata_path) in enumerate(zip(self.audio_files, self.metadata_files)):
+            try:
+                waveform, sr = self._load_audio(audio_path)
+                audio_duration = waveform.shape[1] / sr
+                if self.use_gaussian_augmentation:
+                    events, centres, t_lab = L.region_events(metadata_path, audio_duration, self.I, self.J,
+                                                             self.num_classes)
+                else:
+                    events, t_lab = L.point_events(metadata_path, audio_duration, self.I, self.J, self.num_classes)
+                    centres = None
+                t_mel = 1 + waveform.shape[1] // self.spectrogram_hop_length
+                keep = min(t_mel, t_lab)  # dataset.py:243-249
+                if len(events):  # events beyond the kept frames are cropped with the labels
+                    sel = events[:, 0] < keep
+                    events = events[sel].copy()
+                    events[:, 1] = np.minimum(events[:, 1], keep)
+                    if centres is not None:
+                        centres = centres[sel]
+                    events[:, 0] += total
+                    events[:, 1] += total
+                waves.append((waveform, sr))
+                per_file.append((total, keep, events, centres))
+                total += keep
+            except Exception as e:
+                logger.error(f"Error processing file {idx} ({audio_path}): {str(e)}")
+                raise
+
+        dev = self.device
+        n_ch = None
+        plan = None
+        self.total_frames = total
+        self.file_offsets = [p[0] for p in per_file]
+        self.file_frames = [p[1] for p in per_file]
+        feats = None
+        stats = None
+        for (waveform, sr), (off, keep, _ev, _ce) in zip(waves, per_file):
+            if plan is None or plan.sample_rate != sr:
+                plan = get_plan(self.n_fft, self.spectrogram_hop_length, self.n_mels, sr, dev)
+            c_out = plan.out_channels(_lib_mode(self._mode), waveform.shape[0])
+            if feats is None:
+                n_ch = c_out
+                feats = torch.empty((total, n_ch, self.n_mels), dtype=torch.float32, device=dev)
+                if self._compute_stats:
+                    stats = torch.zeros(2 * n_ch * self.n_mels, dtype=torch.float64, device=dev)
+            elif c_out != n_ch:
+                raise RuntimeError(f"Sizes of tensors must match: {c_out} feature channels vs {n_ch}")
+            if keep == 0:
+                continue
+            x = waveform.to(device=dev, dtype=torch.float32, non_blocking=True).unsqueeze(0)
+            plan.run(x, mode=self._mode, out=feats[off:off + keep].unsqueeze(0), T_out=keep, stats=stats)
+        if feats is None:
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")
+        self.n_channels = n_ch
+        self.stats = stats  # [sum | sum of squares] per (channel, mel) over all kept frames, float64, or None
+        self.events = (np.concatenate([p[2] for p in per_file]) if per_file else np.zeros((0, 4), np.int32))
+        ce = [p[3] for p in per_file if p[3] is not None]
+        self.centres = np.concatenate(ce) if ce else None
+        if self.label_mode == "dense":
+            lab = torch.empty((total, self.total_cells, self.num_classes), dtype=torch.float32, device=dev)
+            L.encode_dense(lab, self.events, self.centres, self.I, self.J)
+        else:
+            lab = None
+        torch.cuda.synchronize(dev)
+        if self.resident == "cpu":
+            feats = feats.cpu()
+            lab = lab.cpu() if lab is not None else None
+        self._features_tcf = feats
+        self.concatenated_labels = lab
+        logger.info(f"Concatenated data: {self.total_frames} total frames")
+        logger.info(f"  Spectrograms shape: {self.concatenated_spectrograms.shape}")
+        if lab is not None:
+            logger.info(f"  Labels shape: {self.concatenated_labels.shape}")
+
+    @property
+    def concatenated_spectrograms(self) -> torch.Tensor:
+        """(C, n_mels, sum T) view, the reference's layout (dataset.py:259)."""
+        return self._features_tcf.permute(1, 2, 0)
+
+    # ------------------------------------------------------------------------------------------
+    def _create_windows(self):
+        """dataset.py:267-317: windows [50k, 50k+250) while 50k < sum T; the tail is padded with 0 features and
+        background labels.  Full windows are views, exactly like the reference."""
+        self.windows = []
+        W, H, T = self.window_length_frames, self.hop_length_frames, self.total_frames
+        start_frame, window_idx = 0, 0
+        while start_frame < T:
+            end_frame = start_frame + W
+            if end_frame <= T:
+                window_spec = self._features_tcf[start_frame:end_frame]
+                window_labels = self.concatenated_labels[start_frame:end_frame] if self.label_mode == "dense" else None
+            else:
+                pad_frames = W - (T - start_frame)
+                f = self._features_tcf
+                spec_pad = torch.zeros((pad_frames, f.shape[1], f.shape[2]), dtype=f.dtype, device=f.device)
+                window_spec = torch.cat([f[start_frame:], spec_pad], dim=0)
+                if self.label_mode == "dense":
+                    l = self.concatenated_labels
+                    label_pad = torch.zeros((pad_frames, self.total_cells, self.num_classes), dtype=l.dtype,
+                                            device=l.device)
+                    label_pad[:, :, self.num_classes - 1] = 1.0
+                    window_labels = torch.cat([l[start_frame:], label_pad], dim=0)
+                else:
+                    window_labels = None
+            self.windows.append({'spectrogram': window_spec, 'labels': window_labels, 'window_idx': window_idx,
+                                 'start_frame': start_frame, 'end_frame': min(end_frame, T)})
+            start_frame += H
+            window_idx += 1
+        logger.info(f"Created {len(self.windows)} windows")
+
+    def __len__(self):
+        return len(self.windows)
+
+    def __getitem__(self, idx):
+        """(spectrogram (250, C, n_mels), labels (250, I*J, M)) — dataset.py:322-330."""
+        window = self.windows[idx]
+        if window['labels'] is None:  # compact mode: paint this single window
+            lab = self.paint_label_windows([window['start_frame']])[0]
+            return window['spectrogram'], lab
+        return window['spectrogram'], window['labels']
+
+    # ------------------------------------------------------------------------------------------
+    def paint_label_windows(self, starts, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Dense labels (n, W, I*J, M) for windows starting at ``starts``, painted on the GPU from the compact
+        event tables (background for frames past the end, like the reference's padding)."""
+        W, T = self.window_length_frames, self.total_frames
+        n = len(starts)
+        if out is None:
+            out = torch.empty((n, W, self.total_cells, self.num_classes), dtype=torch.float32, device=self.device)
+        ev_all, ce_all = self.events, self.centres
+        evs, ces = [], []
+        for w, s in enumerate(starts):
+            if len(ev_all) == 0:
+                continue
+            sel = (ev_all[:, 1] > s) & (ev_all[:, 0] < min(s + W, T))
+            e = ev_all[sel].copy()
+            e[:, 0] = np.maximum(e[:, 0], s) - s + w * W
+            e[:, 1] = np.minimum(e[:, 1], s + W) - s + w * W
+            evs.append(e)
+            if ce_all is not None:
+                ces.append(ce_all[sel])
+        events = np.concatenate(evs) if evs else np.zeros((0, 4), np.int32)
+        centres = np.concatenate(ces) if ces else None
+        L.encode_dense(out.view(n * W, self.total_cells, self.num_classes), events, centres, self.I, self.J)
+        return out
+
+
+def _lib_mode(mode: str) -> int:
+    from .features import MODES
+    return MODES[mode]
+
+
+class DeviceLoader:
+    """On-device replacement for ``DataLoader(SELDDataset)`` (main.py:60-74 builds one with 2 workers and pinned
+    memory; trainer.py only needs ``.dataset``, ``len()`` and iteration — trainer.py:42-47, :165-168).
+    Batches ``(B, 250, C, 64)`` / ``(B, 250, I*J, M)`` are gathered (features) and painted or gathered (labels)
+    in HBM with the window kernels; nothing crosses PCIe per step."""
+
+    def __init__(self, dataset: SELDDataset, batch_size=16, shuffle=False, drop_last=False, generator=None):
+        if dataset.resident != "cuda":
+            raise ValueError("DeviceLoader needs SELDDataset(resident='cuda')")
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, batch_size, shuffle, drop_last
+        self.generator = generator
+        ds = dataset
+        self._starts = torch.tensor([w['start_frame'] for w in ds.windows], dtype=torch.int64)
+        row = ds.n_channels * ds.n_mels
+        self._pad_feat = torch.zeros(row, dtype=torch.float32, device=ds.device)
+        pad_lab = torch.zeros((ds.total_cells, ds.num_classes), dtype=torch.float32, device=ds.device)
+        pad_lab[:, ds.num_classes - 1] = 1.0
+        self._pad_lab = pad_lab.reshape(-1)
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _gather(self, src2d: torch.Tensor, starts_dev: torch.Tensor, pad_row: torch.Tensor, n: int) -> torch.Tensor:
+        W = self.dataset.window_length_frames
+        rows, row_len = src2d.shape
+        out = torch.empty((n, W, row_len), dtype=torch.float32, device=src2d.device)
+        stream = torch.cuda.current_stream(src2d.device).cuda_stream
+        _lib.check(_lib.lib().seld_window_gather(src2d.data_ptr(), rows, row_len, starts_dev.data_ptr(), n, W,
+                                                 pad_row.data_ptr(), out.data_ptr(), stream), "seld_window_gather")
+        return out
+
+    def __iter__(self):
+        ds = self.dataset
+        n = len(ds)
+        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        for i in range(0, n, self.batch_size):
+            idx = order[i:i + self.batch_size]
+            if self.drop_last and len(idx) < self.batch_size:
+                break
+            starts = self._starts[idx]
+            starts_dev = starts.to(ds.device)
+            f = ds._features_tcf
+            spec = self._gather(f.view(f.shape[0], -1), starts_dev, self._pad_feat, len(idx))
+            spec = spec.view(len(idx), ds.window_length_frames, ds.n_channels, ds.n_mels)
+            if ds.label_mode == "dense":
+                l = ds.concatenated_labels
+                lab = self._gather(l.view(l.shape[0], -1), starts_dev, self._pad_lab, len(idx))
+                lab = lab.view(len(idx), ds.window_length_frames, ds.total_cells, ds.num_classes)
+            else:
+                lab = ds.paint_label_windows(starts.tolist())
+            yield spec, lab

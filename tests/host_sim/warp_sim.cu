@@ -55,7 +55,7 @@ static int run(int C, long long N, bool iv, const float* window, const float* fb
             for (int q = 0; q < 4; ++q) {
                 int c[8] = {0};
                 int mx = 0;
-                for (int l = 0; l < 8; ++l) { int r = mt.entries[it * 32 + q * 8 + l].x & 7; mx = std::max(mx, ++c[r]); }
+                for (int l = 0; l < 8; ++l) { int r = (mt.entries[it * 32 + q * 8 + l].x >> 4) & 7; mx = std::max(mx, ++c[r]); }
                 wf += mx; ++cnt;
             }
         fprintf(stderr, "mel schedule: %.3f wavefronts per quarter-warp load (1.0 = conflict-free)\n", wf / cnt);
@@ -65,7 +65,7 @@ static int run(int C, long long N, bool iv, const float* window, const float* fb
     const int C_out = iv ? 7 : C;
     std::vector<float> out((size_t)T * C_out * n_mels, 0.f);
     std::vector<float2> spec((size_t)C * T * NB);
-    std::vector<float4> Q(NB), R(NB);
+    std::vector<float4> Q(NB), R(NB > 528 ? NB : 528);  // R also hosts the 32x33 transpose tile
     float2* Tt = reinterpret_cast<float2*>(R.data());
     static float2 u[32][32];
     for (long long t = 0; t < T; ++t)
@@ -93,7 +93,7 @@ static int run(int C, long long N, bool iv, const float* window, const float* fb
             const bool have_b = nch > 2;
             if (have_b)
                 fft_pair_sim<R1>(u, x + 2 * N, nch > 3 ? x + 3 * N : nullptr, start, N, win.data(), tw.data(), Tt);
-            std::vector<float4> Rn(NB);
+            std::vector<float4> Rn(NB > 528 ? NB : 528);
             for (int lane = 0; lane < R1; ++lane)
                 for (int kh = 0; kh <= 16; ++kh) {
                     if (kh == 16 && lane != 0) break;
@@ -124,7 +124,7 @@ static int run(int C, long long N, bool iv, const float* window, const float* fb
                     const int s = i < mt.la ? 0 : 1;
                     const int2 en = mt.entries[(size_t)i * 32 + lane];
                     float w; memcpy(&w, &en.y, 4);
-                    const float4 q = Q[en.x], r = R[en.x];
+                    const float4 q = Q[en.x >> 4], r = R[en.x >> 4];
                     acc[s][0] = fmaf(w, q.x, acc[s][0]); acc[s][1] = fmaf(w, q.y, acc[s][1]);
                     acc[s][2] = fmaf(w, r.x, acc[s][2]); acc[s][3] = fmaf(w, r.y, acc[s][3]);
                     acc[s][4] = fmaf(w, q.z, acc[s][4]); acc[s][5] = fmaf(w, q.w, acc[s][5]);
