@@ -27,6 +27,7 @@ static int unsupported(const std::string& msg) {
 
 int launch_features(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream);
 int launch_gcc(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream);
+int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream);
 int launch_labels_fill(float* out, long long rows, int cells, int M, cudaStream_t st);
 int launch_labels_paint(float* out, long long rows, int I, int J, int M, const int* events, const double* centres,
                         int n_events, double sigma_az, double sigma_el, cudaStream_t st);
@@ -161,7 +162,19 @@ int seld_features(seld_plan* plan, int mode, const float* d_audio, int64_t clip_
     a.n_items = n_items;
     SELD_CUDA_TRY(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mode == SELD_MODE_LOGMEL_GCC) return launch_gcc(plan, a, st);
+    if (mode == SELD_MODE_LOGMEL_GCC) {  // channels [c_off, c_off+4): log-mel, [c_off+4, c_off+10): GCC-PHAT
+        FeatArgs lm = a;
+        lm.n_out = 4;
+        lm.stats = nullptr;
+        lm.spec = a.spec;
+        int rc = launch_features(plan, false, lm, st);
+        if (rc != SELD_OK) return rc;
+        FeatArgs g = a;
+        g.c_off = c_off + 4;
+        rc = launch_gcc(plan, g, st);
+        if (rc != SELD_OK) return rc;
+        return a.stats ? launch_feature_stats(plan, a, st) : SELD_OK;
+    }
     return launch_features(plan, mode == SELD_MODE_LOGMEL_IV, a, st);
 }
 

@@ -42,8 +42,9 @@ __device__ __forceinline__ void load_raw(float2 (&v)[R1], const float* xa, const
 // window -> pass 1 -> transpose -> pass 2; result in u (lane = k_lo, register = k_hi)
 template <int R1>
 __device__ __forceinline__ void fft_from_raw(float2 (&u)[32], float2 (&v)[R1], const float* s_win, const float2* s_tw,
-                                             float2* T, int lane) {
+                                             float2* T, int lane, bool& a_silent, bool& b_silent) {
     using F = WarpFft<R1>;
+    F::silent_channels(v, a_silent, b_silent);
 #pragma unroll
     for (int j = 0; j < R1; ++j) {
         const float w = s_win[lane + 32 * j];
@@ -146,7 +147,8 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
         float2 u[32];
         const long long spec_cs = a.T_out * NB;  // channel stride of the spectrum dump
         // ================= channel pair (c0, c0+1) =================
-        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane);
+        bool sil_a, sil_b;
+        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, sil_a, sil_b);
         const bool have_b = cur.nch > 2;
         if (have_b)  // request pair b now; it lands while pair a is post-processed
             load_raw<R1>(v, cur.x + 2 * a.chan_stride, cur.nch > 3 ? cur.x + 3 * a.chan_stride : nullptr, cur.start,
@@ -173,44 +175,74 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
                 if (cur.nch > 1) cur.spec[spec_cs + NB - 1] = x1;
             }
         }
+        if (sil_a || sil_b) {  // rare (warp-uniform): a silent channel gets an exactly-zero spectrum
+            const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
+            __syncwarp();
+            for (int k = lane; k < NB; k += 32) {
+                float4 s = Q[k];
+                Q[k] = make_float4(s.x * ka, s.y * ka, s.z * kb, s.w * kb);
+                if (SPEC) {
+                    cur.spec[k] = make_float2(s.x * ka, s.y * ka);
+                    if (cur.nch > 1) cur.spec[spec_cs + k] = make_float2(s.z * kb, s.w * kb);
+                }
+            }
+            __syncwarp();
+        }
         // ================= channel pair (c0+2, c0+3) =================
+        bool sil_c = true, sil_d = true;
         if (have_b) {
-            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane);
+            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, sil_c, sil_d);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) u[i] = make_float2(0.f, 0.f);
             __syncwarp();
         }
-        static_for<16>([&](auto KH) {
-            constexpr int kh = decltype(KH)::value;
-            float2 x2, x3;
-            split_pair<R1, kh>(u, lane, src, x2, x3);
-            const int k = lane + R1 * kh;
-            if (active) {
-                const float4 s = Q[k];
+        auto post_b = [&](auto ZERO) {
+            constexpr bool zero = decltype(ZERO)::value;  // some channel of pair b is silent (rare, warp-uniform)
+            const float kc = sil_c ? 0.f : 1.f, kd = sil_d ? 0.f : 1.f;
+            static_for<16>([&](auto KH) {
+                constexpr int kh = decltype(KH)::value;
+                float2 x2, x3;
+                split_pair<R1, kh>(u, lane, src, x2, x3);
+                if (zero) {
+                    x2 = make_float2(x2.x * kc, x2.y * kc);
+                    x3 = make_float2(x3.x * kd, x3.y * kd);
+                }
+                const int k = lane + R1 * kh;
+                if (active) {
+                    const float4 s = Q[k];
+                    float4 q, r;
+                    bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
+                    Q[k] = q;
+                    R[k] = r;
+                    if (SPEC && have_b) {
+                        cur.spec[2 * spec_cs + k] = x2;
+                        if (cur.nch > 3) cur.spec[3 * spec_cs + k] = x3;
+                    }
+                }
+            });
+            if (lane == 0) {
+                float2 x2, x3;
+                F::unpack(u[16], u[16], x2, x3);
+                if (zero) {
+                    x2 = make_float2(x2.x * kc, x2.y * kc);
+                    x3 = make_float2(x3.x * kd, x3.y * kd);
+                }
+                const float4 s = Q[NB - 1];
                 float4 q, r;
                 bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
-                Q[k] = q;
-                R[k] = r;
+                Q[NB - 1] = q;
+                R[NB - 1] = r;
                 if (SPEC && have_b) {
-                    cur.spec[2 * spec_cs + k] = x2;
-                    if (cur.nch > 3) cur.spec[3 * spec_cs + k] = x3;
+                    cur.spec[2 * spec_cs + NB - 1] = x2;
+                    if (cur.nch > 3) cur.spec[3 * spec_cs + NB - 1] = x3;
                 }
             }
-        });
-        if (lane == 0) {
-            float2 x2, x3;
-            F::unpack(u[16], u[16], x2, x3);
-            const float4 s = Q[NB - 1];
-            float4 q, r;
-            bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
-            Q[NB - 1] = q;
-            R[NB - 1] = r;
-            if (SPEC && have_b) {
-                cur.spec[2 * spec_cs + NB - 1] = x2;
-                if (cur.nch > 3) cur.spec[3 * spec_cs + NB - 1] = x3;
-            }
-        }
+        };
+        if (have_b && (sil_c || sil_d))
+            post_b(std::true_type{});
+        else
+            post_b(std::false_type{});
 
         // ================= next item: request its pair a while the mel gather runs =================
         t += warps_total;

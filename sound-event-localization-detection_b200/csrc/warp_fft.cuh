@@ -64,9 +64,54 @@ struct WarpFft {
     }
     static SELD_HD void pass2(float2 (&u)[32]) { Dft<32, false>::run(u); }
 
+    // ---- inverse transform pieces (GCC-PHAT), unnormalised: x[t] = sum_k G[k] exp(+2 pi i k t / N) ----
+    // same data flow as the forward transform with conjugated twiddles; lane = t_lo after the transpose.
+    static SELD_HD void pass1_inv(float2 (&v)[R1], const float2* tw_lane) {
+        Dft<R1, true>::run(v);
+        static_for<R1 - 1>([&](auto K) {
+            constexpr int k = decltype(K)::value + 1;
+            v[k] = cmul_conj(v[k], tw_lane[k * 32]);
+        });
+    }
+    // pruned second pass: only t_hi = 0 (lags t_lo) and t_hi = 31 (lags t_lo - 32) are needed
+    static SELD_HD void pass2_inv_pruned(const float2 (&w)[32], float2& lag_pos, float2& lag_neg) {
+        float2 a[32], b[32];
+        static_for<32>([&](auto Nn) {
+            constexpr int n = decltype(Nn)::value;
+            a[n] = w[n];
+            b[n] = mul_w<n, 32, false>(w[n]);  // exp(+2 pi i 31 n / 32) = W_32^n
+        });
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1)
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                a[i] = cadd(a[i], a[i + s]);
+                b[i] = cadd(b[i], b[i + s]);
+            }
+        lag_pos = a[0];
+        lag_neg = b[0];
+    }
+
     // lane that holds the mirror bin of this lane's bins
     static SELD_HD int partner_lane(int lane) { return (lane == 0 || lane >= R1) ? 0 : R1 - lane; }
     static SELD_HD int bin_of(int lane, int k_hi) { return lane + R1 * k_hi; }
+
+    // Is either channel of the packed pair identically zero in this frame?  (OR of the raw sample bits, sign
+    // ignored, then a warp vote.)  A silent channel must come out as an exactly-zero spectrum like the
+    // reference's separate FFT — the split below would otherwise leave the rounding asymmetry of the other
+    // channel (~1e-7 relative) in it.
+#ifdef __CUDACC__
+    static __device__ __forceinline__ void silent_channels(const float2 (&v)[R1], bool& a_silent, bool& b_silent) {
+        unsigned ba = 0u, bb = 0u;
+        static_for<R1>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            ba |= __float_as_uint(v[j].x);
+            bb |= __float_as_uint(v[j].y);
+        });
+        a_silent = !__any_sync(0xffffffffu, (ba << 1) != 0u);
+        b_silent = !__any_sync(0xffffffffu, (bb << 1) != 0u);
+    }
+#endif
 
     // split Z = Xa + i Xb (window pre-scaled by 1/2, so no factor here)
     static SELD_HD void unpack(float2 z, float2 p, float2& xa, float2& xb) {

@@ -150,3 +150,52 @@ def test_errors_are_exceptions(sb):
         sb.extract_features(torch.zeros(1, 3, 4800, device="cuda"), 24000, 1024, 480, 64, mode="logmel_iv")
     with pytest.raises((ValueError, sb.SeldError)):
         sb.extract_features(torch.zeros(1, 4, 4800), 24000, 1024, 480, 64)  # CPU tensor: no CPU path
+
+
+# ---- MIC format: 4 log-mel + 6 GCC-PHAT (north_star kernel 3; no reference code — parity unpinned) ----
+@pytest.mark.parametrize("name", ["noise_1s", "noise_n97440", "int16_noise", "impulse_first", "zeros", "sine_1k_1e-4_ch0"])
+def test_mic_gcc_vs_oracle(sb, golden_features, name):
+    kind, n, seed = cases.AUDIO_CASES[name]
+    x = cases.make_audio(kind, n, seed)
+    y = _run(sb, x, 1024, mode="logmel_gcc")[0]  # (T, 10, 64)
+    want = of.mic_features(x, 24000, 1024, 480, 64, fb=golden_features["fb_1024"]).transpose(2, 0, 1)
+    assert y.shape == want.shape
+    assert np.abs(y[:, :4] - want[:, :4]).max() <= TOL_DB
+    # tolerance: 1e-4 relative to the largest |cc| of the frame (PHAT-normalised correlations peak at <= 1)
+    scale = np.abs(want[:, 4:]).max(axis=(1, 2), keepdims=True)
+    if kind == "sine":
+        # channels 1..3 are exactly 0 -> R == 0 -> phase 1 -> delta at lag 0 for every pair
+        assert np.abs(y[:, 4:] - want[:, 4:]).max() <= 1e-6 and (y[:, 4:, 32] > 0.999999).all()
+    else:
+        assert (np.abs(y[:, 4:] - want[:, 4:]) <= TOL_REL * np.maximum(scale, 1e-12)).all()
+
+
+def test_gcc_peak_at_delay(sb):
+    rng = np.random.default_rng(3)
+    s = rng.standard_normal(24000 + 80)
+    d = 7
+    x = np.stack([s[40:40 + 24000], s[40 - d:40 - d + 24000], s[40:40 + 24000], s[45:45 + 24000]]).astype(np.float32)
+    y = _run(sb, x, 1024, mode="logmel_gcc")[0][5:45, 4:]  # (frames, 6, 64)
+    assert (y[:, 0].argmax(-1) == 32 + d).all() and (y[:, 1].argmax(-1) == 32).all() and (y[:, 2].argmax(-1) == 27).all()
+
+
+def test_gcc_needs_1024_and_4_channels(sb):
+    with pytest.raises(sb.SeldError):
+        sb.extract_features(torch.zeros(1, 4, 4800, device="cuda"), 24000, 960, 480, 64, mode="logmel_gcc")
+    with pytest.raises(sb.SeldError):
+        sb.extract_features(torch.zeros(1, 2, 4800, device="cuda"), 24000, 1024, 480, 64, mode="logmel_gcc")
+
+
+def test_dead_channel_next_to_full_scale_signal(sb):
+    """A silent channel packed with a loud one must still read exactly -100 dB (the reference transforms every
+    channel separately); its IV contribution is exactly 0."""
+    n = 9600
+    x = np.zeros((4, n), np.float32)
+    x[0] = np.sin(2 * np.pi * 3000.0 * np.arange(n) / 24000).astype(np.float32)
+    x[3] = 0.9 * np.sin(2 * np.pi * 5000.0 * np.arange(n) / 24000).astype(np.float32)
+    for n_fft in (1024, 960):
+        y = _run(sb, x, n_fft, mode="logmel_iv")[0]
+        assert (y[:, 1] == -100.0).all() and (y[:, 2] == -100.0).all()
+        assert (y[:, 4] == 0).all() and (y[:, 5] == 0).all()
+        want = of.logmel_iv(x, 24000, n_fft, 480, 64).transpose(2, 0, 1)
+        assert np.abs(y[:, :4] - want[:, :4]).max() <= TOL_DB
