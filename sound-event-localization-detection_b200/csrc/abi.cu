@@ -110,8 +110,8 @@ int seld_plan_create(seld_plan** out, int device, int n_fft, int hop, int n_mels
     p->dev.twiddle = reinterpret_cast<const float2*>(d + off_tw);
     p->dev.mel_entries = reinterpret_cast<const int2*>(d + off_mel);
     p->dev.mel_idx = reinterpret_cast<const int*>(d + off_idx);
-    // per warp: Q rows + max(R rows, 32x33 float2 transpose tile)
-    p->feat_smem = total + (size_t)kFeatWarps * (n_bins + std::max(n_bins, 528)) * sizeof(float4);
+    p->table_bytes = total;
+    p->warp_smem = (size_t)(n_bins + std::max(n_bins, 528)) * sizeof(float4);
     *out = p;
     return SELD_OK;
 }

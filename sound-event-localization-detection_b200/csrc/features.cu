@@ -10,6 +10,8 @@
 // Latency hiding with only 12 warps per SM (shared memory bound) is done by register prefetch: the raw
 // samples of channel pair b are requested before the post-processing of pair a, and the samples of the NEXT
 // frame's pair a before the mel gather of the current frame, when the FFT registers are dead.
+#include <cstdlib>
+
 #include "seld_common.h"
 #include "warp_fft.cuh"
 
@@ -42,12 +44,14 @@ __device__ __forceinline__ void load_raw(float2 (&v)[R1], const float* xa, const
 // window -> pass 1 -> transpose -> pass 2; result in u (lane = k_lo, register = k_hi)
 template <int R1>
 __device__ __forceinline__ void fft_from_raw(float2 (&u)[32], float2 (&v)[R1], const float* s_win, const float2* s_tw,
-                                             float2* T, int lane, bool& a_silent, bool& b_silent) {
+                                             float2* T, int lane, unsigned& bits_a, unsigned& bits_b) {
     using F = WarpFft<R1>;
-    F::silent_channels(v, a_silent, b_silent);
+    bits_a = bits_b = 0u;  // OR of the raw sample bits: all-zero channel detection (voted on after the FFT)
 #pragma unroll
     for (int j = 0; j < R1; ++j) {
         const float w = s_win[lane + 32 * j];
+        bits_a |= __float_as_uint(v[j].x);
+        bits_b |= __float_as_uint(v[j].y);
         v[j].x *= w;
         v[j].y *= w;
     }
@@ -82,8 +86,8 @@ struct ItemCtx {
     bool valid;         // t < T_b (padding rows of a ragged batch are written as 0)
 };
 
-template <int R1, bool IV, bool SPEC>
-__global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p, FeatArgs a) {
+template <int R1, bool IV, bool SPEC, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, FeatArgs a) {
     using F = WarpFft<R1>;
     constexpr int N = F::N, NB = F::NB;
     constexpr int NCH = IV ? 7 : 4;
@@ -113,9 +117,9 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
     const bool active = lane < R1;  // lanes >= R1 (n_fft 960) own no bins
 
     // ---- work distribution: item = (b*G + g)*T_out + t, items of one warp are warps_total apart ----
-    const unsigned warps_total = gridDim.x * kFeatWarps;
+    const unsigned warps_total = gridDim.x * WARPS;
     const unsigned n_items = (unsigned)a.n_items, T_out = (unsigned)a.T_out;
-    unsigned item = blockIdx.x * kFeatWarps + warp;
+    unsigned item = blockIdx.x * WARPS + warp;
     if (item >= n_items) return;
     unsigned bg = item / T_out, t = item - bg * T_out;
     long long len_cache_b = -1, len_cache = a.n_samples;
@@ -147,8 +151,8 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
         float2 u[32];
         const long long spec_cs = a.T_out * NB;  // channel stride of the spectrum dump
         // ================= channel pair (c0, c0+1) =================
-        bool sil_a, sil_b;
-        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, sil_a, sil_b);
+        unsigned bits_a, bits_b;
+        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, bits_a, bits_b);
         const bool have_b = cur.nch > 2;
         if (have_b)  // request pair b now; it lands while pair a is post-processed
             load_raw<R1>(v, cur.x + 2 * a.chan_stride, cur.nch > 3 ? cur.x + 3 * a.chan_stride : nullptr, cur.start,
@@ -175,7 +179,11 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
                 if (cur.nch > 1) cur.spec[spec_cs + NB - 1] = x1;
             }
         }
-        if (sil_a || sil_b) {  // rare (warp-uniform): a silent channel gets an exactly-zero spectrum
+        // A silent channel must come out as an exactly-zero spectrum like the reference's separate FFT; the
+        // split leaves the rounding asymmetry of the other channel (~1e-7 relative) in it.
+        const bool sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
+        const bool sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
+        if (sil_a || sil_b) {  // rare (warp-uniform)
             const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
             __syncwarp();
             for (int k = lane; k < NB; k += 32) {
@@ -189,60 +197,68 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p,
             __syncwarp();
         }
         // ================= channel pair (c0+2, c0+3) =================
-        bool sil_c = true, sil_d = true;
+        unsigned bits_c = 0u, bits_d = 0u;
         if (have_b) {
-            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, sil_c, sil_d);
+            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, bits_c, bits_d);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) u[i] = make_float2(0.f, 0.f);
             __syncwarp();
         }
-        auto post_b = [&](auto ZERO) {
-            constexpr bool zero = decltype(ZERO)::value;  // some channel of pair b is silent (rare, warp-uniform)
-            const float kc = sil_c ? 0.f : 1.f, kd = sil_d ? 0.f : 1.f;
-            static_for<16>([&](auto KH) {
-                constexpr int kh = decltype(KH)::value;
-                float2 x2, x3;
-                split_pair<R1, kh>(u, lane, src, x2, x3);
-                if (zero) {
-                    x2 = make_float2(x2.x * kc, x2.y * kc);
-                    x3 = make_float2(x3.x * kd, x3.y * kd);
-                }
-                const int k = lane + R1 * kh;
-                if (active) {
-                    const float4 s = Q[k];
-                    float4 q, r;
-                    bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
-                    Q[k] = q;
-                    R[k] = r;
-                    if (SPEC && have_b) {
-                        cur.spec[2 * spec_cs + k] = x2;
-                        if (cur.nch > 3) cur.spec[3 * spec_cs + k] = x3;
-                    }
-                }
-            });
-            if (lane == 0) {
-                float2 x2, x3;
-                F::unpack(u[16], u[16], x2, x3);
-                if (zero) {
-                    x2 = make_float2(x2.x * kc, x2.y * kc);
-                    x3 = make_float2(x3.x * kd, x3.y * kd);
-                }
-                const float4 s = Q[NB - 1];
+        static_for<16>([&](auto KH) {
+            constexpr int kh = decltype(KH)::value;
+            float2 x2, x3;
+            split_pair<R1, kh>(u, lane, src, x2, x3);
+            const int k = lane + R1 * kh;
+            if (active) {
+                const float4 s = Q[k];
                 float4 q, r;
                 bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
-                Q[NB - 1] = q;
-                R[NB - 1] = r;
+                Q[k] = q;
+                R[k] = r;
                 if (SPEC && have_b) {
-                    cur.spec[2 * spec_cs + NB - 1] = x2;
-                    if (cur.nch > 3) cur.spec[3 * spec_cs + NB - 1] = x3;
+                    cur.spec[2 * spec_cs + k] = x2;
+                    if (cur.nch > 3) cur.spec[3 * spec_cs + k] = x3;
                 }
             }
-        };
-        if (have_b && (sil_c || sil_d))
-            post_b(std::true_type{});
-        else
-            post_b(std::false_type{});
+        });
+        if (lane == 0) {
+            float2 x2, x3;
+            F::unpack(u[16], u[16], x2, x3);
+            const float4 s = Q[NB - 1];
+            float4 q, r;
+            bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
+            Q[NB - 1] = q;
+            R[NB - 1] = r;
+            if (SPEC && have_b) {
+                cur.spec[2 * spec_cs + NB - 1] = x2;
+                if (cur.nch > 3) cur.spec[3 * spec_cs + NB - 1] = x3;
+            }
+        }
+        const bool sil_c = !__any_sync(0xffffffffu, (bits_c << 1) != 0u);
+        const bool sil_d = !__any_sync(0xffffffffu, (bits_d << 1) != 0u);
+        if (have_b && (sil_c || sil_d)) {  // rare (warp-uniform): redo the rows with the silent channel at exactly 0
+            __syncwarp();
+            for (int k = lane; k < NB; k += 32) {
+                const float4 q = Q[k], r = R[k];
+                const float p2 = sil_c ? 0.f : r.x, p3 = sil_d ? 0.f : r.y;
+                float4 qn = make_float4(q.x, q.y, 0.f, 0.f), rn = make_float4(p2, p3, 0.f, 0.f);
+                if (IV) {
+                    const float e_old = kEpsIV + q.x + (q.y + r.x + r.y) * (1.0f / 3.0f);
+                    const float e_new = kEpsIV + q.x + (q.y + p2 + p3) * (1.0f / 3.0f);
+                    const float g = e_old / e_new;  // numerators I_c = (I_c / E_old) * E_old
+                    qn.z = q.z * g;
+                    qn.w = sil_c ? 0.f : q.w * g;
+                    rn.z = sil_d ? 0.f : r.z * g;
+                }
+                Q[k] = qn;
+                R[k] = rn;
+                if (SPEC) {
+                    if (sil_c) cur.spec[2 * spec_cs + k] = make_float2(0.f, 0.f);
+                    if (sil_d && cur.nch > 3) cur.spec[3 * spec_cs + k] = make_float2(0.f, 0.f);
+                }
+            }
+        }
 
         // ================= next item: request its pair a while the mel gather runs =================
         t += warps_total;
@@ -356,16 +372,31 @@ __global__ void __launch_bounds__(512) feature_stats_kernel(const float* __restr
     }
 }
 
-template <int R1, bool IV, bool SPEC>
+template <int R1, bool IV, bool SPEC, int WARPS>
 static int launch_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    auto kern = features_kernel<R1, IV, SPEC>;
-    SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->feat_smem));
-    long long ctas = (a.n_items + kFeatWarps - 1) / kFeatWarps;
+    auto kern = features_kernel<R1, IV, SPEC, WARPS>;
+    const size_t smem = plan->table_bytes + (size_t)WARPS * plan->warp_smem;
+    SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = (a.n_items + WARPS - 1) / WARPS;
     if (ctas > plan->num_sms) ctas = plan->num_sms;
     if (ctas < 1) return SELD_OK;
-    kern<<<(unsigned)ctas, kFeatWarps * 32, plan->feat_smem, stream>>>(plan->dev, a);
+    kern<<<(unsigned)ctas, WARPS * 32, smem, stream>>>(plan->dev, a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
+}
+
+// warps per CTA: 12 fills the 227 KB of shared memory (168 registers/thread); SELD_FEAT_WARPS=8|10 trades
+// occupancy for registers and L1 (tuning knob, read once)
+template <int R1, bool IV, bool SPEC>
+static int launch_w(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
+    static const int warps = [] {
+        const char* e = getenv("SELD_FEAT_WARPS");
+        const int w = e ? atoi(e) : kFeatWarps;
+        return (w == 8 || w == 10) ? w : kFeatWarps;
+    }();
+    if (!SPEC && warps == 10) return launch_one<R1, IV, SPEC, 10>(plan, a, stream);
+    if (!SPEC && warps == 8) return launch_one<R1, IV, SPEC, 8>(plan, a, stream);
+    return launch_one<R1, IV, SPEC, kFeatWarps>(plan, a, stream);
 }
 
 int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
@@ -384,11 +415,11 @@ int launch_features(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStrea
     const bool sp = a.spec != nullptr;
     int rc;
     if (plan->dev.r1 == 32) {
-        if (iv) rc = sp ? launch_one<32, true, true>(plan, a, stream) : launch_one<32, true, false>(plan, a, stream);
-        else rc = sp ? launch_one<32, false, true>(plan, a, stream) : launch_one<32, false, false>(plan, a, stream);
+        if (iv) rc = sp ? launch_w<32, true, true>(plan, a, stream) : launch_w<32, true, false>(plan, a, stream);
+        else rc = sp ? launch_w<32, false, true>(plan, a, stream) : launch_w<32, false, false>(plan, a, stream);
     } else {
-        if (iv) rc = sp ? launch_one<30, true, true>(plan, a, stream) : launch_one<30, true, false>(plan, a, stream);
-        else rc = sp ? launch_one<30, false, true>(plan, a, stream) : launch_one<30, false, false>(plan, a, stream);
+        if (iv) rc = sp ? launch_w<30, true, true>(plan, a, stream) : launch_w<30, true, false>(plan, a, stream);
+        else rc = sp ? launch_w<30, false, true>(plan, a, stream) : launch_w<30, false, false>(plan, a, stream);
     }
     if (rc != SELD_OK) return rc;
     if (a.stats) return launch_feature_stats(plan, a, stream);

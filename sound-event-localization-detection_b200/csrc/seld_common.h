@@ -46,7 +46,8 @@ struct seld_plan {
     int num_sms;
     seld::PlanDev dev;
     void* d_blob;       // one allocation holding all tables
-    size_t feat_smem;   // dynamic smem bytes of the feature kernel
+    size_t table_bytes; // constant tables at the start of the feature kernel's dynamic smem
+    size_t warp_smem;   // + this many bytes per warp (Q rows + max(R rows, transpose tile))
 };
 
 #define SELD_CUDA_TRY(expr)                                            \

