@@ -26,6 +26,7 @@ static int unsupported(const std::string& msg) {
 }
 
 int launch_features(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream);
+bool v3_filterbank_matches(int n_fft, const float* fb, int n_mels);
 int launch_gcc(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream);
 int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream);
 int launch_labels_fill(float* out, long long rows, int cells, int M, cudaStream_t st);
@@ -112,6 +113,7 @@ int seld_plan_create(seld_plan** out, int device, int n_fft, int hop, int n_mels
     p->dev.mel_idx = reinterpret_cast<const int*>(d + off_idx);
     p->table_bytes = total;
     p->warp_smem = (size_t)(n_bins + std::max(n_bins, 528)) * sizeof(float4);
+    p->v3_ok = v3_filterbank_matches(n_fft, h_fb, n_mels);
     *out = p;
     return SELD_OK;
 }

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
 // x (B, T_out, F) float32; for the columns [col0, col0 + ncols): stats[f] += sum, stats[F + f] += sum of
 // squares over rows t < frames[b] (or t < 1 + len_b/hop when frames is null).
 // CTA = 64 columns x 8 row lanes over a slab of kStatRows rows: every warp reads 128 contiguous bytes per
-// row, 4 rows in flight per thread; float partials over <= 32 rows, then double across row lanes and CTAs.
+// row, 4 rows in flight per thread; float64 accumulation throughout.
 constexpr int kStatRows = 256;
 __global__ void __launch_bounds__(512) feature_stats_kernel(const float* __restrict__ x, long long T_out, int F,
                                                             int col0, int ncols, int B, const int* __restrict__ frames,
@@ -347,18 +347,18 @@ __global__ void __launch_bounds__(512) feature_stats_kernel(const float* __restr
     }
     __syncthreads();
     const int j = blockIdx.y * 64 + threadIdx.x;
-    float cs = 0.f, css = 0.f;
+    double cs = 0.0, css = 0.0;  // float64 throughout: std = sqrt(E[x^2] - mean^2) amplifies the error of the sums
     if (j < ncols) {
         const float* px = x + r0 * F + col0 + j;
 #pragma unroll 4
         for (int r = threadIdx.y; r < n_rows; r += 8) {
-            const float v = s_valid[r] ? __ldg(px + (long long)r * F) : 0.f;
+            const double v = s_valid[r] ? (double)__ldg(px + (long long)r * F) : 0.0;
             cs += v;
-            css = fmaf(v, v, css);
+            css = fma(v, v, css);
         }
     }
-    s_sum[threadIdx.y][threadIdx.x] = (double)cs;
-    s_sq[threadIdx.y][threadIdx.x] = (double)css;
+    s_sum[threadIdx.y][threadIdx.x] = cs;
+    s_sq[threadIdx.y][threadIdx.x] = css;
     __syncthreads();
     if (threadIdx.y == 0 && j < ncols) {
         double s = 0.0, ss = 0.0;
@@ -411,9 +411,24 @@ int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t 
     return SELD_OK;
 }
 
+int launch_features_v3(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream);
+
+// SELD_FEAT_IMPL=v2 forces the generic kernel (A/B measurements; read per call so one process can time both)
+static bool v3_enabled() {
+    const char* e = getenv("SELD_FEAT_IMPL");
+    return !(e && e[0] == 'v' && e[1] == '2');
+}
+
 int launch_features(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream) {
     const bool sp = a.spec != nullptr;
     int rc;
+    // fast path: the reference's own configurations (4 channels, baked 64-mel HTK bank), 16-byte aligned rows
+    if (plan->v3_ok && a.C == 4 && !sp && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && v3_enabled()) {
+        rc = launch_features_v3(plan, iv, a, stream);
+        if (rc != SELD_OK) return rc;
+        if (a.stats) return launch_feature_stats(plan, a, stream);
+        return SELD_OK;
+    }
     if (plan->dev.r1 == 32) {
         if (iv) rc = sp ? launch_w<32, true, true>(plan, a, stream) : launch_w<32, true, false>(plan, a, stream);
         else rc = sp ? launch_w<32, false, true>(plan, a, stream) : launch_w<32, false, false>(plan, a, stream);

@@ -1,0 +1,468 @@
+// v3 of the fused feature kernel (K1+K2): framing + Hann + real FFT (two channels per complex FFT) + power +
+// FOA intensity vectors + mel projection + 10*log10 for the reference's own configurations
+// (4 channels, 64 HTK mels, n_fft 1024 or 960 — reference dataset.py:27-58 with config.py:85-87).
+// Anything else (other channel counts, other filterbanks, spectrum dumps) runs on the generic kernel in
+// features.cu.
+//
+// What bounds this path on B200 is not HBM but the SM's shared-memory datapath (128 B/clk) and the FP32
+// pipe; v3 is organised around shared-memory wavefronts per frame:
+//   * warps work in groups of four.  Phase A: every warp transforms one frame (all four channels, two
+//     packed complex FFTs) exactly like v2, but leaves its per-bin features as seven PLANES
+//     V[c][k] (P0 P1 P2 P3 I1/E I2/E I3/E) in its own shared-memory region.  The spectra of the first
+//     channel pair are parked in planes 0..3 (same lane, same bin: in place), the transpose tile lives
+//     behind them where planes 4..6 go later.
+//   * Phase B (after a 128-thread named barrier): the four warps project the group's four frames onto the
+//     mel filters.  Lane = (frame, channel), so all lanes walk the SAME bins: the filterbank is baked into
+//     the instruction stream (mel_baked.h: weights are FFMA immediates, filter boundaries are straight-line
+//     code), every plane word is read exactly once (no gather tables, no padding, no bank conflicts) and
+//     each warp owns a quarter of the filters.  Results go to global memory as 16-byte stores.
+#include "mel_baked.h"
+#include "seld_common.h"
+#include "warp_fft.cuh"
+
+namespace seld {
+
+constexpr int kV3Warps = 12;  // 3 groups of 4 warps; 1 CTA per SM (shared-memory bound)
+
+template <int R1>
+struct V3Layout {
+    using F = WarpFft<R1>;
+    static constexpr int NB = F::NB;                         // 513 / 481
+    // plane pitch = 4 (mod 8) words: in the mel phase lane (f, c) reads the float4 at word f*REGION + c*PITCH + k;
+    // the 8 lanes of a quarter-warp (one f, c = 0..7) then hit 8 different 16-byte bank groups.
+    static constexpr int PITCH = NB + ((4 - NB % 8) + 8) % 8;  // 516 / 484
+    static constexpr int TILE_OFF = 4 * PITCH;               // the transpose tile sits behind the four parking planes
+    static constexpr int TILE_WORDS = 2 * R1 * F::TP;        // R1 rows of 33 float2
+    static constexpr int REGION = TILE_OFF + TILE_WORDS;     // >= 7 planes
+    // behind the seven planes: the frame's finished output row (7 x 64, channel pitch 65), staged by the mel phase
+    // and copied out as full 128-byte lines by the owning warp.  Frame slot f starts at OUT_OFF + out_skew(f)
+    // so that lane (f, c) lands on bank 8 f + c + m.
+    static constexpr int OUT_OFF = 7 * PITCH, OUT_PITCH = 65;
+    static __device__ __forceinline__ int out_skew(int f) { return (8 * f - f * REGION) & 31; }
+    static_assert(PITCH % 8 == 4 && REGION % 4 == 0 && REGION >= OUT_OFF + 31 + 7 * OUT_PITCH, "region layout");
+};
+
+struct V3Meta {       // per frame slot of a group, written by the owning warp before the barrier
+    float* out_row;   // out[b, t, c_off, 0]
+    int valid;        // t < frames of the clip (else the row is written as 0)
+    int write;        // the item exists at all
+};
+
+#ifdef SELD_V3_LOCKSTEP  // experiment: all groups of the CTA move through the phases together
+__device__ __forceinline__ void group_barrier(int) { __syncthreads(); }
+#else
+__device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+#endif
+
+// edge frames (reflect padding, torch.stft center=True): rare, kept out of line
+template <int R1>
+__device__ __noinline__ void v3_load_edge(float2 (&v)[R1], const float* xa, const float* xb, long long start,
+                                          long long len, int lane) {
+    using F = WarpFft<R1>;
+#pragma unroll 4
+    for (int j = 0; j < R1; ++j) {
+        const long long idx = F::reflect(start + lane + 32 * j, len);
+        v[j] = make_float2(__ldg(xa + idx), __ldg(xb + idx));
+    }
+}
+
+template <int R1>
+__device__ __forceinline__ void v3_load_raw(float2 (&v)[R1], const float* xa, const float* xb, long long start,
+                                            long long len, int lane) {
+    using F = WarpFft<R1>;
+    if ((start >= 0) && (start + F::N <= len)) {
+        const float* pa = xa + start + lane;
+        const float* pb = xb + start + lane;
+#ifdef SELD_ABL_NOLOAD
+#pragma unroll
+        for (int j = 0; j < R1; ++j) v[j] = make_float2(__int_as_float(0x3f000000 + j + lane + (int)start), __int_as_float(0x3e000000 + 3 * j + (int)(size_t)pb));
+#else
+#pragma unroll
+        for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(pa + 32 * j), __ldg(pb + 32 * j));
+#endif
+    } else {  // via a scratch array so that v itself never has its address taken (it must stay in registers)
+        float2 tmp[R1];
+        v3_load_edge<R1>(tmp, xa, xb, start, len, lane);
+#pragma unroll
+        for (int j = 0; j < R1; ++j) v[j] = tmp[j];
+    }
+}
+
+// ask L2 for the 128-byte lines of a channel pair's frame (lane l: line l of each channel); no registers held
+template <int R1>
+__device__ __forceinline__ void v3_prefetch_l2(const float* xa, const float* xb, long long start, long long len, int lane) {
+    long long o = start + 32 * lane;
+    o = o < 0 ? 0 : o;
+    if (lane < R1 && o < len) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xa + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + o));
+    }
+}
+
+// ---- mel projection of one filter chunk for lane (frame, channel) -------------------------------
+template <int NFFT, int CH>
+__device__ __forceinline__ void v3_mel_chunk(const float* __restrict__ vp, float* __restrict__ orow) {
+    using MB = MelBaked<NFFT>;
+    constexpr int M_LO = MB::chunk_m[CH], M_HI = MB::chunk_m[CH + 1];
+    constexpr int K0 = MB::chunk_k0[CH], K1 = MB::chunk_k1[CH];
+    // filters of even / odd index (filters two apart never overlap) x even / odd bins (two FMA chains per filter)
+    float acc00 = 0.f, acc01 = 0.f, acc10 = 0.f, acc11 = 0.f;
+    auto contribute = [&](auto Mc, auto Kc, auto Sel, float v) {
+        constexpr int m = decltype(Mc)::value, k = decltype(Kc)::value;
+        constexpr float w = decltype(Sel)::value ? MB::w1[k] : MB::w0[k];
+        if constexpr (m >= M_LO && m < M_HI) {
+            float& acc = (m & 1) ? ((k & 1) ? acc11 : acc10) : ((k & 1) ? acc01 : acc00);
+            if constexpr (k == MB::first[m] || k == MB::first[m] + 1) acc = w * v;
+            else acc = fmaf(w, v, acc);
+            if constexpr (k == MB::last[m]) {
+                float sum;
+                if constexpr (MB::last[m] == MB::first[m]) sum = acc;
+                else sum = ((m & 1) ? acc10 : acc00) + ((m & 1) ? acc11 : acc01);
+                orow[m] = sum;  // raw mel energy / mel-binned IV; the copy-out applies 10 log10 and row validity
+            }
+        }
+    };
+    constexpr int G0 = K0 & ~3, NG = ((K1 + 3) & ~3) - G0;
+    static_for<NG / 4>([&](auto Gi) {
+        constexpr int g = G0 + 4 * decltype(Gi)::value;
+        const float4 v4 = *reinterpret_cast<const float4*>(vp + g);
+        static_for<4>([&](auto I) {
+            constexpr int k = g + decltype(I)::value;
+            if constexpr (k >= K0 && k < K1) {
+                constexpr int ma = MB::m0[k], mb = MB::m1[k];
+                constexpr bool use_a = ma >= M_LO && ma < M_HI, use_b = mb >= M_LO && mb < M_HI;
+                const float v = decltype(I)::value == 0 ? v4.x : decltype(I)::value == 1 ? v4.y : decltype(I)::value == 2 ? v4.z : v4.w;
+                if constexpr (use_a)
+                    contribute(std::integral_constant<int, (ma < 0 ? 0 : ma)>{}, std::integral_constant<int, k>{},
+                               std::integral_constant<int, 0>{}, v);
+                if constexpr (use_b)
+                    contribute(std::integral_constant<int, (mb < 0 ? 0 : mb)>{}, std::integral_constant<int, k>{},
+                               std::integral_constant<int, 1>{}, v);
+            }
+        });
+    });
+}
+
+struct V3Ctx {        // one frame: clip b, frame t
+    unsigned b, t;
+    long long len;    // samples of the clip
+    int valid, exists;
+};
+
+template <int R1, bool IV>
+__global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p, FeatArgs a) {
+    using F = WarpFft<R1>;
+    using L = V3Layout<R1>;
+    constexpr int N = F::N, NB = F::NB;
+    constexpr int NCH = IV ? 7 : 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_win = reinterpret_cast<float*>(smem_raw);
+    float2* s_tw = reinterpret_cast<float2*>(s_win + N);
+    V3Meta* s_meta = reinterpret_cast<V3Meta*>(s_tw + R1 * 32);
+    float* s_regions = reinterpret_cast<float*>(s_meta + kV3Warps);
+
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_win[i] = p.window[i];
+    for (int i = threadIdx.x; i < R1 * 32; i += blockDim.x) s_tw[i] = p.twiddle[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int group = warp >> 2, wi = warp & 3;
+    float* region = s_regions + warp * L::REGION;
+    float* gregion = s_regions + (group * 4) * L::REGION;
+    float2* T = reinterpret_cast<float2*>(region + L::TILE_OFF);
+    const int src = F::partner_lane(lane);
+    const bool active = R1 == 32 || lane < R1;
+    const int bar_id = 1 + group;
+    constexpr int G = kV3Warps / 4;
+
+    const long long n_items = a.n_items, T_out = a.T_out;
+    const long long n_gitems = (n_items + 3) >> 2;
+    long long gidx = (long long)blockIdx.x * G + group;
+    const long long gstride = (long long)gridDim.x * G;
+#ifdef SELD_V3_LOCKSTEP
+    if ((long long)blockIdx.x * G >= n_gitems) return;
+#else
+    if (gidx >= n_gitems) return;  // whole group leaves together
+#endif
+
+    const unsigned n_items_u = (unsigned)n_items, T_out_u = (unsigned)T_out;
+    const long long frames_all = 1 + a.n_samples / p.hop;
+    auto make_ctx = [&](long long item) {
+        V3Ctx c;
+        c.exists = item < n_items;
+        const unsigned it = c.exists ? (unsigned)item : 0u;
+        c.b = it / T_out_u;
+        c.t = it - c.b * T_out_u;
+        c.len = a.lengths ? a.lengths[c.b] : a.n_samples;
+        const long long frames = a.lengths ? 1 + c.len / p.hop : frames_all;
+        c.valid = c.exists && (long long)c.t < frames;
+        return c;
+    };
+    auto chan0 = [&](const V3Ctx& c) { return a.audio + (long long)c.b * a.clip_stride; };
+    auto frame_start = [&](const V3Ctx& c) { return c.valid ? (long long)c.t * p.hop - F::HALF : 0ll; };
+
+    // copy this warp's staged output row (7 x 64 floats) to global memory, 128 bytes per store
+    // (10 log10 of the power channels happens here; rows beyond the clip's last frame are written as 0)
+    float* prev_row = nullptr;
+    bool prev_valid = false;
+    const float* stage = region + L::OUT_OFF + L::out_skew(wi) + lane;
+    auto copy_out = [&]() {
+        if (prev_row) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float x0 = stage[c * L::OUT_PITCH], x1 = stage[c * L::OUT_PITCH + 32];
+                if (c < 4) {
+                    x0 = power_to_db(x0);
+                    x1 = power_to_db(x1);
+                }
+                prev_row[c * 64 + lane] = prev_valid ? x0 : 0.f;
+                prev_row[c * 64 + 32 + lane] = prev_valid ? x1 : 0.f;
+            }
+        }
+    };
+
+    V3Ctx cur = make_ctx(4 * gidx + wi);
+    float2 v[R1];  // raw samples of the channel pair about to be transformed, requested one phase ahead
+    v3_load_raw<R1>(v, chan0(cur), chan0(cur) + a.chan_stride, frame_start(cur), cur.len, lane);
+
+    while (true) {
+        const long long gnext = gidx + gstride;
+#ifdef SELD_V3_LOCKSTEP
+        const bool more = gnext - group < n_gitems;  // CTA-uniform trip count; surplus items do not exist
+#else
+        const bool more = gnext < n_gitems;
+#endif
+        V3Ctx nxt = cur;
+        if (more) nxt = make_ctx(4 * gnext + wi);
+
+#pragma unroll 1
+        for (int pr = 0; pr < 2; ++pr) {
+            // ---- window + pass 1 + twiddle (registers only) ----
+            unsigned bits_a = 0u, bits_b = 0u;
+#pragma unroll
+            for (int j = 0; j < R1; ++j) {
+                const float w = s_win[lane + 32 * j];
+                bits_a |= __float_as_uint(v[j].x);
+                bits_b |= __float_as_uint(v[j].y);
+                v[j].x *= w;
+                v[j].y *= w;
+            }
+            F::pass1(v, s_tw + lane);
+            // the other warps of the group have finished reading this region (previous mel phase)
+            if (pr == 0) {
+                group_barrier(bar_id);
+                copy_out();  // the previous frame's row is complete (all four filter chunks staged)
+            }
+            __syncwarp();
+            F::t_store(v, T, lane);
+            __syncwarp();
+            float2 u[32];
+            F::t_load(u, T, lane);
+            __syncwarp();
+            if (pr == 0) {  // v is dead: request pair b of this frame, it lands during pass 2 and the unpacking
+                const float* xb = chan0(cur) + 2 * a.chan_stride;
+                v3_load_raw<R1>(v, xb, xb + a.chan_stride, frame_start(cur), cur.len, lane);
+            }
+            F::pass2(u);
+            const bool sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
+            const bool sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
+
+#ifdef SELD_ABL_NOPOST
+            if (pr < 2) {
+                float sx = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sx += u[i].x * u[i].y;
+                if (sx == 123.456f) region[lane] = sx;
+            } else
+#endif
+            if (pr == 0) {
+                // ---- park X0, X1 in planes 0..3 (read back by the same lane) ----
+                static_for<16>([&](auto KH) {
+                    constexpr int kh = decltype(KH)::value;
+                    float2 x0, x1;
+                    {
+                        const float2 z = u[kh], m = u[31 - kh];
+                        float2 q;
+                        q.x = __shfl_sync(0xffffffffu, m.x, src);
+                        q.y = __shfl_sync(0xffffffffu, m.y, src);
+                        const float2 own = u[(32 - kh) & 31];
+                        q.x = lane == 0 ? own.x : q.x;
+                        q.y = lane == 0 ? own.y : q.y;
+                        F::unpack(z, q, x0, x1);
+                    }
+                    const int k = lane + R1 * kh;
+                    if (active) {  // parked in planes 0..3, read back by the same lane
+                        region[k] = x0.x;
+                        region[L::PITCH + k] = x0.y;
+                        region[2 * L::PITCH + k] = x1.x;
+                        region[3 * L::PITCH + k] = x1.y;
+                    }
+                });
+                if (lane == 0) {
+                    float2 x0, x1;
+                    F::unpack(u[16], u[16], x0, x1);
+                    const int k = NB - 1;
+                    region[k] = x0.x;
+                    region[L::PITCH + k] = x0.y;
+                    region[2 * L::PITCH + k] = x1.x;
+                    region[3 * L::PITCH + k] = x1.y;
+                }
+                if (sil_a || sil_b) {  // rare: a digitally silent channel must give an exactly-zero spectrum
+                    const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
+                    __syncwarp();
+                    for (int k = lane; k < NB; k += 32) {
+                        region[k] *= ka;
+                        region[L::PITCH + k] *= ka;
+                        region[2 * L::PITCH + k] *= kb;
+                        region[3 * L::PITCH + k] *= kb;
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // ---- per-bin features -> seven planes (planes 4..6 overlay the dead transpose tile) ----
+                static_for<16>([&](auto KH) {
+                    constexpr int kh = decltype(KH)::value;
+                    float2 x2, x3;
+                    {
+                        const float2 z = u[kh], m = u[31 - kh];
+                        float2 q;
+                        q.x = __shfl_sync(0xffffffffu, m.x, src);
+                        q.y = __shfl_sync(0xffffffffu, m.y, src);
+                        const float2 own = u[(32 - kh) & 31];
+                        q.x = lane == 0 ? own.x : q.x;
+                        q.y = lane == 0 ? own.y : q.y;
+                        F::unpack(z, q, x2, x3);
+                    }
+                    const int k = lane + R1 * kh;
+                    if (active) {
+                        const float2 x0 = make_float2(region[k], region[L::PITCH + k]);
+                        const float2 x1 = make_float2(region[2 * L::PITCH + k], region[3 * L::PITCH + k]);
+                        float4 q, r;
+                        bin_features<IV>(x0, x1, x2, x3, q, r);
+                        region[k] = q.x;
+                        region[L::PITCH + k] = q.y;
+                        region[2 * L::PITCH + k] = r.x;
+                        region[3 * L::PITCH + k] = r.y;
+                        if (IV) {
+                            region[4 * L::PITCH + k] = q.z;
+                            region[5 * L::PITCH + k] = q.w;
+                            region[6 * L::PITCH + k] = r.z;
+                        }
+                    }
+                });
+                if (lane == 0) {
+                    float2 x2, x3;
+                    F::unpack(u[16], u[16], x2, x3);
+                    const int k = NB - 1;
+                    const float2 x0 = make_float2(region[k], region[L::PITCH + k]);
+                    const float2 x1 = make_float2(region[2 * L::PITCH + k], region[3 * L::PITCH + k]);
+                    float4 q, r;
+                    bin_features<IV>(x0, x1, x2, x3, q, r);
+                    region[k] = q.x;
+                    region[L::PITCH + k] = q.y;
+                    region[2 * L::PITCH + k] = r.x;
+                    region[3 * L::PITCH + k] = r.y;
+                    if (IV) {
+                        region[4 * L::PITCH + k] = q.z;
+                        region[5 * L::PITCH + k] = q.w;
+                        region[6 * L::PITCH + k] = r.z;
+                    }
+                }
+                if (sil_a || sil_b) {  // rare: redo the planes with the silent channel (2 = a, 3 = b) at exactly 0
+                    __syncwarp();
+                    for (int k = lane; k < NB; k += 32) {
+                        const float p0 = region[k], p1 = region[L::PITCH + k], p2o = region[2 * L::PITCH + k], p3o = region[3 * L::PITCH + k];
+                        const float p2 = sil_a ? 0.f : p2o, p3 = sil_b ? 0.f : p3o;
+                        region[2 * L::PITCH + k] = p2;
+                        region[3 * L::PITCH + k] = p3;
+                        if (IV) {
+                            const float e_old = kEpsIV + p0 + (p1 + p2o + p3o) * (1.0f / 3.0f);
+                            const float e_new = kEpsIV + p0 + (p1 + p2 + p3) * (1.0f / 3.0f);
+                            const float g = e_old / e_new;
+                            region[4 * L::PITCH + k] *= g;
+                            region[5 * L::PITCH + k] = sil_a ? 0.f : region[5 * L::PITCH + k] * g;
+                            region[6 * L::PITCH + k] = sil_b ? 0.f : region[6 * L::PITCH + k] * g;
+                        }
+                    }
+                }
+            }
+        }
+        if (more)  // request pair a of the next frame, it lands during the mel phase
+            v3_load_raw<R1>(v, chan0(nxt), chan0(nxt) + a.chan_stride, frame_start(nxt), nxt.len, lane);
+        prev_valid = cur.valid;
+        prev_row = cur.exists ? a.out + (((long long)cur.b * T_out + cur.t) * a.C_out + a.c_off) * 64 + 0 : nullptr;
+        if (lane == 0) {
+            V3Meta m;
+            m.out_row = a.out + (((long long)cur.b * T_out + cur.t) * a.C_out + a.c_off) * 64;
+            m.valid = cur.valid;
+            m.write = cur.exists;
+            s_meta[warp] = m;
+        }
+        group_barrier(bar_id);  // the four frames of the group are in their planes
+
+        // ---- mel phase: lane = (frame, channel); this warp owns filter chunk wi ----
+#ifndef SELD_ABL_NOMEL
+        {
+            const int f = lane >> 3, c = lane & 7;
+            const V3Meta m = s_meta[group * 4 + f];
+            if (c < NCH && m.write) {
+                const float* vp = gregion + f * L::REGION + c * L::PITCH;
+                float* orow = gregion + f * L::REGION + L::OUT_OFF + L::out_skew(f) + c * L::OUT_PITCH;
+                switch (wi) {
+                    case 0: v3_mel_chunk<N, 0>(vp, orow); break;
+                    case 1: v3_mel_chunk<N, 1>(vp, orow); break;
+                    case 2: v3_mel_chunk<N, 2>(vp, orow); break;
+                    default: v3_mel_chunk<N, 3>(vp, orow); break;
+                }
+            }
+        }
+#endif
+        if (!more) break;
+        gidx = gnext;
+        cur = nxt;
+    }
+    group_barrier(bar_id);
+    copy_out();
+}
+
+// Does the caller's filterbank equal the baked one bit for bit?  (host, at plan creation)
+template <int NFFT>
+static bool fb_matches(const float* fb, int n_mels) {
+    using MB = MelBaked<NFFT>;
+    if (n_mels != MB::N_MELS) return false;
+    for (int k = 0; k < MB::NB; ++k)
+        for (int m = 0; m < n_mels; ++m) {
+            float want = 0.f;
+            if (m == MB::m0[k]) want = MB::w0[k];
+            if (m == MB::m1[k]) want = MB::w1[k];
+            if (fb[(size_t)k * n_mels + m] != want) return false;
+        }
+    return true;
+}
+bool v3_filterbank_matches(int n_fft, const float* fb, int n_mels) {
+    return n_fft == 1024 ? fb_matches<1024>(fb, n_mels) : n_fft == 960 ? fb_matches<960>(fb, n_mels) : false;
+}
+
+template <int R1, bool IV>
+static int launch_v3_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
+    using L = V3Layout<R1>;
+    auto kern = features_v3_kernel<R1, IV>;
+    const size_t smem = sizeof(float) * (R1 * 32) + sizeof(float2) * (R1 * 32) + sizeof(V3Meta) * kV3Warps +
+                        sizeof(float) * (size_t)kV3Warps * L::REGION;
+    SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_gitems = (a.n_items + 3) / 4;
+    long long ctas = (n_gitems + kV3Warps / 4 - 1) / (kV3Warps / 4);
+    if (ctas > plan->num_sms) ctas = plan->num_sms;
+    if (ctas < 1) return SELD_OK;
+    kern<<<(unsigned)ctas, kV3Warps * 32, smem, stream>>>(plan->dev, a);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
+int launch_features_v3(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream) {
+    if (plan->dev.r1 == 32) return iv ? launch_v3_one<32, true>(plan, a, stream) : launch_v3_one<32, false>(plan, a, stream);
+    return iv ? launch_v3_one<30, true>(plan, a, stream) : launch_v3_one<30, false>(plan, a, stream);
+}
+
+}  // namespace seld

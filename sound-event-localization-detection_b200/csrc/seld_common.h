@@ -48,6 +48,7 @@ struct seld_plan {
     void* d_blob;       // one allocation holding all tables
     size_t table_bytes; // constant tables at the start of the feature kernel's dynamic smem
     size_t warp_smem;   // + this many bytes per warp (Q rows + max(R rows, transpose tile))
+    bool v3_ok;         // the filterbank equals the baked one of mel_baked.h: the v3 kernel may be used
 };
 
 #define SELD_CUDA_TRY(expr)                                            \
