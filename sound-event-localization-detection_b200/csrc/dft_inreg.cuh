@@ -62,8 +62,40 @@ SELD_HD void static_for(F&& f) {
 }
 
 // ---- complex helpers ------------------------------------------------------------------------------
-SELD_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-SELD_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add / subtract.  On sm_100a these are ONE packed instruction each (add/sub.rn.f32x2 -> FADD2): the FP32
+// pipe does the same work, but the butterflies — three quarters of the FFT — take half the issue slots.
+// ptxas folds the +-i rotations around them into operand swizzles (.F32x2.LO_HI) and negations.
+SELD_HD float2 cadd(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+SELD_HD float2 csub(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// (a.x * w, a.y * w): one FMUL2 with a broadcast scalar operand
+SELD_HD float2 cscale(float2 a, float w) {
+#ifdef __CUDA_ARCH__
+    float2 r;
+    asm("{.reg .b64 ra, rw, rc; mov.b64 ra, {%2, %3}; mov.b64 rw, {%4, %4}; mul.rn.f32x2 rc, ra, rw; mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(w));
+    return r;
+#else
+    return make_float2(a.x * w, a.y * w);
+#endif
+}
 SELD_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 SELD_HD float2 cmul_conj(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
 SELD_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)

@@ -32,7 +32,12 @@ struct V3Layout {
     // the 8 lanes of a quarter-warp (one f, c = 0..7) then hit 8 different 16-byte bank groups.
     static constexpr int PITCH = NB + ((4 - NB % 8) + 8) % 8;  // 516 / 484
     static constexpr int TILE_OFF = 4 * PITCH;               // the transpose tile sits behind the four parking planes
-    static constexpr int TILE_WORDS = 2 * R1 * F::TP;        // R1 rows of 33 float2
+    static constexpr int TP = 34;                            // tile row pitch in float2: 272 B = 17 x 16 B, see below
+    static constexpr int TILE_WORDS = 2 * R1 * TP;           // R1 rows (one per reader lane) of 34 float2
+    // constant tables, one row per LANE so that a lane fetches its values with 128-bit loads; row pitches of
+    // 9 x 16 B and 17 x 16 B put the 8 lanes of a quarter-warp on 8 different 16-byte bank groups
+    static constexpr int WIN_PITCH = 36;                     // floats:  window[lane + 32 j] / 2 at [lane][j]
+    static constexpr int TW_PITCH = 34;                      // float2s: W_N^(lane k) at [lane][k]
     static constexpr int REGION = TILE_OFF + TILE_WORDS;     // >= 7 planes
     // behind the seven planes: the frame's finished output row (7 x 64, channel pitch 65), staged by the mel phase
     // and copied out as full 128-byte lines by the owning warp.  Frame slot f starts at OUT_OFF + out_skew(f)
@@ -157,12 +162,18 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
     constexpr int NCH = IV ? 7 : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);
-    float2* s_tw = reinterpret_cast<float2*>(s_win + N);
-    V3Meta* s_meta = reinterpret_cast<V3Meta*>(s_tw + R1 * 32);
+    float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * L::WIN_PITCH);
+    V3Meta* s_meta = reinterpret_cast<V3Meta*>(s_tw + 32 * L::TW_PITCH);
     float* s_regions = reinterpret_cast<float*>(s_meta + kV3Warps);
 
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s_win[i] = p.window[i];
-    for (int i = threadIdx.x; i < R1 * 32; i += blockDim.x) s_tw[i] = p.twiddle[i];
+    for (int i = threadIdx.x; i < 32 * L::WIN_PITCH; i += blockDim.x) {
+        const int l = i / L::WIN_PITCH, j = i - l * L::WIN_PITCH;
+        s_win[i] = j < R1 ? p.window[l + 32 * j] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * L::TW_PITCH; i += blockDim.x) {
+        const int l = i / L::TW_PITCH, k = i - l * L::TW_PITCH;
+        s_tw[i] = k < R1 ? p.twiddle[k * 32 + l] : make_float2(0.f, 0.f);
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -240,25 +251,54 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
         for (int pr = 0; pr < 2; ++pr) {
             // ---- window + pass 1 + twiddle (registers only) ----
             unsigned bits_a = 0u, bits_b = 0u;
-#pragma unroll
-            for (int j = 0; j < R1; ++j) {
-                const float w = s_win[lane + 32 * j];
-                bits_a |= __float_as_uint(v[j].x);
-                bits_b |= __float_as_uint(v[j].y);
-                v[j].x *= w;
-                v[j].y *= w;
+            {
+                const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * L::WIN_PITCH);
+                static_for<(R1 + 3) / 4>([&](auto Jq) {
+                    constexpr int j0 = 4 * decltype(Jq)::value;
+                    const float4 w4 = wrow[j0 / 4];
+                    static_for<4>([&](auto Ji) {
+                        constexpr int j = j0 + decltype(Ji)::value;
+                        if constexpr (j < R1) {
+                            const float w = decltype(Ji)::value == 0 ? w4.x : decltype(Ji)::value == 1 ? w4.y : decltype(Ji)::value == 2 ? w4.z : w4.w;
+                            bits_a |= __float_as_uint(v[j].x);
+                            bits_b |= __float_as_uint(v[j].y);
+                            v[j] = cscale(v[j], w);
+                        }
+                    });
+                });
             }
-            F::pass1(v, s_tw + lane);
+            Dft<R1, false>::run(v);
+            {
+                const float4* trow = reinterpret_cast<const float4*>(s_tw + lane * L::TW_PITCH);
+                static_for<(R1 + 1) / 2>([&](auto Kq) {
+                    constexpr int k0 = 2 * decltype(Kq)::value;
+                    const float4 t4 = trow[k0 / 2];
+                    if constexpr (k0 >= 1) v[k0] = cmul(v[k0], make_float2(t4.x, t4.y));
+                    if constexpr (k0 + 1 < R1) v[k0 + 1] = cmul(v[k0 + 1], make_float2(t4.z, t4.w));
+                });
+            }
             // the other warps of the group have finished reading this region (previous mel phase)
             if (pr == 0) {
                 group_barrier(bar_id);
                 copy_out();  // the previous frame's row is complete (all four filter chunks staged)
             }
             __syncwarp();
-            F::t_store(v, T, lane);
+            static_for<R1>([&](auto K) {  // row k belongs to reader lane k; column = this lane
+                constexpr int k = decltype(K)::value;
+                T[k * L::TP + lane] = v[k];
+            });
             __syncwarp();
             float2 u[32];
-            F::t_load(u, T, lane);
+            {
+                const float4* urow = reinterpret_cast<const float4*>(T + (active ? lane : 0) * L::TP);
+                static_for<16>([&](auto Nq) {
+                    constexpr int n = 2 * decltype(Nq)::value;
+                    const float4 t4 = urow[n / 2];
+                    u[n] = make_float2(t4.x, t4.y);
+                    u[n + 1] = make_float2(t4.z, t4.w);
+                });
+                if (!active) static_for<32>([&](auto Nn) { u[decltype(Nn)::value] = make_float2(0.f, 0.f); });
+            }
             __syncwarp();
             if (pr == 0) {  // v is dead: request pair b of this frame, it lands during pass 2 and the unpacking
                 const float* xb = chan0(cur) + 2 * a.chan_stride;
@@ -448,7 +488,7 @@ template <int R1, bool IV>
 static int launch_v3_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
     using L = V3Layout<R1>;
     auto kern = features_v3_kernel<R1, IV>;
-    const size_t smem = sizeof(float) * (R1 * 32) + sizeof(float2) * (R1 * 32) + sizeof(V3Meta) * kV3Warps +
+    const size_t smem = sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH) + sizeof(V3Meta) * kV3Warps +
                         sizeof(float) * (size_t)kV3Warps * L::REGION;
     SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_gitems = (a.n_items + 3) / 4;
