@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the SELD feature front-end hot path (BASELINE.json configs[1]).
 
-Step = one pass of the fused STFT + log-mel + IV kernel over a batch of 256 synthetic 60 s 4-channel 24 kHz
-clips per GPU (n_fft 1024, hop 480, 64 mel -> 7-channel features), inputs resident in HBM.
+Step = one pass of the feature front-end over a batch of 256 synthetic 60 s 4-channel 24 kHz clips per GPU
+(n_fft 1024, hop 480, 64 mel -> 7-channel log-mel + IV features), inputs resident in HBM: the fused feature
+kernel, the scaler-partials kernel and (N > 1) the all-reduce of those partials.
 Metric: audio clip-seconds per second, whole job (all ranks).  One JSON line on rank 0.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -190,9 +191,16 @@ def main():
     stat_frames = torch.full((B,), T - 1, dtype=torch.int32, device=dev)  # the frames SELDDataset keeps
     plan = seld_b200.get_plan(N_FFT, HOP, N_MELS, SR, dev)
 
-    def step():
-        plan.run(audio, mode="logmel_iv", out=out, stats=stats, stat_frames=stat_frames)
-        if world > 1:  # the path's only collective: scaler partials (sum, sum of squares), ~7 KB fp64
+    def step(kev=None):
+        # kernel 1 (dominant): fused framing + Hann + FFT + power + IV + mel + log; bracketed by its own events
+        if kev is not None:
+            kev[0].record()
+        plan.run(audio, mode="logmel_iv", out=out)
+        if kev is not None:
+            kev[1].record()
+        # kernel 2: scaler partials (per-feature sum / sum of squares over the kept frames)
+        plan.accumulate_stats(out, stats, stat_frames=stat_frames)
+        if world > 1:  # the path's only collective: ~7 KB of fp64 partials
             dist.all_reduce(stats)
 
     def barrier():
@@ -207,15 +215,17 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stats.zero_()
     barrier()
     ev[0].record()
     for i in range(args.steps):
-        step()
+        step(kev[i])
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps  # feature kernel alone, same timed region
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -223,14 +233,12 @@ def main():
     clip_s_per_step = B * CLIP_SECONDS
     value = world * clip_s_per_step * args.steps / (total_ms / 1e3)
 
-    # dominant kernel (the only kernel of the step): per-launch duration from the same events; with N > 1
-    # the tiny all-reduce sits between launches, so N = 1 is the clean roofline figure
-    kern_ms = total_ms / args.steps
+    # dominant kernel: the fused feature kernel, timed by its own CUDA events inside the timed region
     peak, peak_src = peaks()
     achieved = BYTES_PER_CLIP_SECOND * clip_s_per_step / (kern_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "seld::features_kernel<32,IV,STATS>",
-                "algorithmic_bytes_per_launch": BYTES_PER_CLIP_SECOND * clip_s_per_step}
+                "traffic": None, "peak_source": peak_src, "kernel": "seld::features_v3_kernel<32, IV>",
+                "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_PER_CLIP_SECOND * clip_s_per_step}
     tfile = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
     if os.path.exists(tfile):
         try:
@@ -281,7 +289,7 @@ def main():
                        "l2": "inputs 5.9 GB per step >> 126 MB L2 (no flush needed)",
                        "collective": "all_reduce(fp64 scaler partials, 7 KB) per step" if world > 1 else "none (1 GPU)",
                        "timing": "CUDA events on the launch stream, max over ranks"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

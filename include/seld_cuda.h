@@ -84,6 +84,15 @@ SELD_API int seld_features(seld_plan* plan, int mode, const float* d_audio, int6
                   int C_out, int c_off, double* d_stats, const int32_t* d_stat_frames, float* d_spec,
                   void* stream);
 
+/* Scaler partials of an already computed feature tensor (the accumulation seld_features performs when given
+ * d_stats, as a call of its own): for the channels [c_off, c_off + n_channels) of d_feat (B, T_out, C_out, n_mels)
+ * ADD per-feature sum and sum of squares over the frames t < d_stat_frames[b] (NULL: t < 1 + len_b / hop with
+ * len_b = d_lengths[b], or n_samples when d_lengths is NULL) into d_stats (float64[2 * C_out * n_mels]).
+ * Not in the reference. */
+SELD_API int seld_feature_stats(seld_plan* plan, const float* d_feat, int B, int64_t T_out, int C_out, int c_off,
+                       int n_channels, int64_t n_samples, const int64_t* d_lengths, const int32_t* d_stat_frames,
+                       double* d_stats, void* stream);
+
 /* (x - mean) * inv_std in place over (rows, n_feat) float32; mean/inv_std float32[n_feat].
  * The scaler apply step. */
 SELD_API int seld_scaler_apply(float* d_x, int64_t rows, int n_feat, const float* d_mean, const float* d_inv_std,

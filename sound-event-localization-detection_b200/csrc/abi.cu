@@ -180,6 +180,29 @@ int seld_features(seld_plan* plan, int mode, const float* d_audio, int64_t clip_
     return launch_features(plan, mode == SELD_MODE_LOGMEL_IV, a, st);
 }
 
+int seld_feature_stats(seld_plan* plan, const float* d_feat, int B, int64_t T_out, int C_out, int c_off, int n_channels,
+                       int64_t n_samples, const int64_t* d_lengths, const int32_t* d_stat_frames, double* d_stats,
+                       void* stream) {
+    if (!plan) return bad_arg("seld_feature_stats: null plan");
+    if (!d_feat || !d_stats) return bad_arg("seld_feature_stats: null device pointer");
+    if (B < 0 || T_out < 0 || C_out < 1 || c_off < 0 || n_channels < 1 || c_off + n_channels > C_out)
+        return bad_arg("seld_feature_stats: bad size");
+    if (B == 0 || T_out == 0) return SELD_OK;
+    FeatArgs a{};
+    a.out = const_cast<float*>(d_feat);
+    a.B = B;
+    a.T_out = T_out;
+    a.C_out = C_out;
+    a.c_off = c_off;
+    a.n_out = n_channels;
+    a.n_samples = n_samples;
+    a.lengths = reinterpret_cast<const long long*>(d_lengths);
+    a.stat_frames = d_stat_frames;
+    a.stats = d_stats;
+    SELD_CUDA_TRY(cudaSetDevice(plan->device));
+    return launch_feature_stats(plan, a, static_cast<cudaStream_t>(stream));
+}
+
 int seld_scaler_apply(float* d_x, int64_t rows, int n_feat, const float* d_mean, const float* d_inv_std,
                       void* stream) {
     if (!d_x || !d_mean || !d_inv_std) return bad_arg("seld_scaler_apply: null pointer");

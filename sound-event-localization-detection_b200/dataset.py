@@ -268,6 +268,15 @@ class SELDDataset(Dataset):
         return out
 
 
+def shard_clips(n_clips: int, rank: int, world_size: int):
+    """Contiguous block [lo, hi) of the sorted file list owned by ``rank``: clips are independent
+    (reference dataset.py:218-252), so ranks never exchange audio or features; contiguous blocks keep the reference's
+    concatenation order (dataset.py:125-128) inside each rank.  Sizes differ by at most one clip."""
+    base, extra = divmod(int(n_clips), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
 def _lib_mode(mode: str) -> int:
     from .features import MODES
     return MODES[mode]

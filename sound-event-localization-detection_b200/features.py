@@ -115,6 +115,26 @@ class FeaturePlan:
         return out
 
 
+    def accumulate_stats(self, feats: torch.Tensor, stats: torch.Tensor, n_samples: int = 0,
+                         lengths: torch.Tensor | None = None, stat_frames: torch.Tensor | None = None, c_off: int = 0,
+                         n_channels: int | None = None) -> torch.Tensor:
+        """Scaler partials of a finished feature tensor (B, T_out, C_out, n_mels): what ``run(stats=...)`` adds,
+        as a call of its own (``seld_feature_stats``)."""
+        if feats.dtype != torch.float32 or not feats.is_contiguous() or feats.dim() != 4 or feats.device != self.device:
+            raise ValueError("feats must be a contiguous float32 (B, T_out, C_out, n_mels) tensor on the plan's device")
+        B, T_out, C_out, M = feats.shape
+        if M != self.n_mels or stats.dtype != torch.float64 or stats.numel() != 2 * C_out * M or stats.device != self.device:
+            raise ValueError("stats must hold 2 * C_out * n_mels float64 values on the plan's device")
+        if stat_frames is None and lengths is None and n_samples <= 0:
+            raise ValueError("give stat_frames, lengths or n_samples")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().seld_feature_stats(
+                self._handle, feats.data_ptr(), B, T_out, C_out, c_off, C_out - c_off if n_channels is None else n_channels,
+                int(n_samples), _lib.ptr(lengths), _lib.ptr(stat_frames), stats.data_ptr(), stream), "seld_feature_stats")
+        return stats
+
+
 _plans: dict = {}
 _plans_lock = threading.Lock()
 

@@ -1,0 +1,131 @@
+"""GPU parity of BOTH feature kernels through the C ABI: the v3 fast path (reference configurations: 4 channels,
+baked 64-mel HTK bank) and the generic kernel (SELD_FEAT_IMPL=v2 forces it), against the golden outputs of the
+reference's audio_to_mel_spectrogram (dataset.py:27-58) and the fp64 IV oracle, plus size-independent properties at
+BASELINE's full clip size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import features as of
+
+pytestmark = pytest.mark.gpu
+TOL_DB, TOL_REL = 1e-3, 1e-4  # BASELINE.json north_star: <= 1e-3 dB on log-mel, <= 1e-4 relative on IV / GCC
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import seld_b200
+    return seld_b200
+
+
+@pytest.fixture(params=["v3", "v2"])
+def impl(request):
+    old = os.environ.get("SELD_FEAT_IMPL")
+    os.environ["SELD_FEAT_IMPL"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("SELD_FEAT_IMPL", None)
+    else:
+        os.environ["SELD_FEAT_IMPL"] = old
+
+
+def _feat(sb, x, n_fft, mode, **kw):
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    return sb.extract_features(t, 24000, n_fft, 480, 64, mode=mode, **kw).cpu().numpy()
+
+
+@pytest.mark.parametrize("n_fft", [1024, 960])
+@pytest.mark.parametrize("name", ["noise_1s", "noise_n24479", "impulse_first", "impulse_last", "sine_1k_1e-4_ch0", "int16_noise", "loud_noise", "zeros"])
+def test_both_kernels_vs_reference_golden(sb, golden_features, impl, name, n_fft):
+    if name not in cases.AUDIO_CASES:
+        pytest.skip("case not in the golden set")
+    kind, n, seed = cases.AUDIO_CASES[name]
+    x = cases.make_audio(kind, n, seed)
+    y = _feat(sb, x, n_fft, "logmel")[0]  # (T, 4, 64)
+    ref = golden_features[f"{name}/logmel_{n_fft}"]  # (4, 64, T) from the reference itself
+    assert y.shape == (ref.shape[2], 4, 64)
+    assert np.abs(y.transpose(1, 2, 0) - ref).max() <= TOL_DB
+
+
+@pytest.mark.parametrize("n_fft", [1024, 960])
+def test_iv_both_kernels_vs_oracle(sb, impl, n_fft):
+    x = cases.make_audio("noise", 24000 + 123, 77)
+    y = _feat(sb, x, n_fft, "logmel_iv")[0]
+    want = of.logmel_iv(x, 24000, n_fft, 480, 64).transpose(2, 0, 1)
+    assert np.abs(y[:, :4] - want[:, :4]).max() <= TOL_DB
+    assert np.abs(y[:, 4:] - want[:, 4:]).max() / np.abs(want[:, 4:]).max() <= TOL_REL
+
+
+@pytest.mark.parametrize("t_out", [1, 2, 3, 5, 50, 51])
+def test_frame_capacity_not_multiple_of_group(sb, impl, t_out):
+    """v3 works on groups of four frames; any frame capacity must give the same rows and touch nothing else."""
+    x = cases.make_audio("noise", 24000, 5)
+    full = _feat(sb, x, 1024, "logmel_iv")[0]
+    out = torch.full((1, t_out + 2, 7, 64), 7.0, dtype=torch.float32, device="cuda")
+    sb.extract_features(torch.from_numpy(x).cuda().unsqueeze(0), 24000, 1024, 480, 64, mode="logmel_iv",
+                        out=out[:, :t_out], T_out=t_out)
+    got = out.cpu().numpy()[0]
+    assert np.array_equal(got[:t_out], full[:t_out])
+    assert (got[t_out:] == 7.0).all()
+
+
+def test_v3_equals_generic_kernel_on_ragged_batch(sb):
+    """Same batch through both kernels: ragged lengths, strided clips, rows past a clip's end written as 0."""
+    rng = np.random.default_rng(3)
+    ns = [24000, 1000, 24479, 12345, 600]
+    nmax = max(ns)
+    buf = torch.zeros((len(ns), 4, nmax + 5), dtype=torch.float32)
+    for i, n in enumerate(ns):
+        buf[i, :, :n] = torch.from_numpy((0.1 * rng.standard_normal((4, n))).astype(np.float32))
+    buf[3, 2] = 0.0  # a digitally silent channel inside a live clip
+    audio = buf.cuda()[:, :, :nmax]
+    lengths = torch.tensor(ns, dtype=torch.int64, device="cuda")
+    res = {}
+    for impl in ("v3", "v2"):
+        os.environ["SELD_FEAT_IMPL"] = impl
+        res[impl] = sb.extract_features(audio, 24000, 1024, 480, 64, mode="logmel_iv", lengths=lengths).cpu().numpy()
+    os.environ.pop("SELD_FEAT_IMPL", None)
+    a, b = res["v3"], res["v2"]
+    assert np.abs(a[..., :4, :] - b[..., :4, :]).max() <= 1e-4      # dB
+    assert np.abs(a[..., 4:, :] - b[..., 4:, :]).max() <= 1e-5      # IV, |.| <= 1
+    for i, n in enumerate(ns):
+        assert (a[i, 1 + n // 480:] == 0).all()
+    assert (a[3, : 1 + ns[3] // 480, 2] == -100.0).all()            # silent channel: exactly amin
+
+
+def test_full_size_properties_config1_clip(sb, impl):
+    """BASELINE-sized clip (60 s, 4 ch): size-independent properties instead of an oracle run.
+    Power is quadratic: scaling the input by g shifts every log-mel value by 20 log10 g and leaves IV unchanged;
+    swapping the dipole channels permutes the IV channels."""
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(4, 24000 * 60, generator=g)
+    y = _feat(sb, x.numpy(), 1024, "logmel_iv")[0]
+    assert y.shape == (3001, 7, 64) and np.isfinite(y).all()
+    y2 = _feat(sb, (4.0 * x).numpy(), 1024, "logmel_iv")[0]
+    assert np.abs((y2[:, :4] - y[:, :4]) - 20 * np.log10(4.0)).max() <= 2e-4
+    assert np.abs(y2[:, 4:] - y[:, 4:]).max() <= 1e-5
+    xs = x[[0, 2, 1, 3]]
+    ys = _feat(sb, xs.numpy(), 1024, "logmel_iv")[0]
+    assert np.abs(ys[:, [0, 2, 1, 3]] - y[:, :4]).max() <= 1e-4
+    assert np.abs(ys[:, [5, 4, 6]] - y[:, 4:]).max() <= 1e-5
+
+
+def test_feature_stats_call_matches_fused_accumulation(sb):
+    x = np.stack([cases.make_audio("noise", 48000, 60 + i) for i in range(3)])
+    T = 1 + 48000 // 480
+    stat_frames = torch.tensor([T - 1, T, 10], dtype=torch.int32, device="cuda")
+    plan = sb.get_plan(1024, 480, 64, 24000, "cuda")
+    audio = torch.from_numpy(x).cuda()
+    s1 = torch.zeros(2 * 7 * 64, dtype=torch.float64, device="cuda")
+    out = plan.run(audio, mode="logmel_iv", stats=s1, stat_frames=stat_frames)
+    s2 = torch.zeros_like(s1)
+    plan.accumulate_stats(out, s2, stat_frames=stat_frames)
+    assert torch.equal(s1, s2) or torch.allclose(s1, s2, rtol=1e-12, atol=1e-9)
+    rows = np.concatenate([out[0, :T - 1].cpu(), out[1, :T].cpu(), out[2, :10].cpu()]).astype(np.float64).reshape(-1, 448)
+    assert np.allclose(s2.cpu().numpy()[:448], rows.sum(0), rtol=1e-9, atol=1e-6)
+    assert np.allclose(s2.cpu().numpy()[448:], (rows * rows).sum(0), rtol=1e-9, atol=1e-6)
