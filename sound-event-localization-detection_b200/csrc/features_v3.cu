@@ -53,11 +53,17 @@ struct V3Meta {       // per frame slot of a group, written by the owning warp b
     int write;        // the item exists at all
 };
 
-#ifdef SELD_V3_LOCKSTEP  // experiment: all groups of the CTA move through the phases together
-__device__ __forceinline__ void group_barrier(int) { __syncthreads(); }
-#else
+// (s.x^2 + d.y^2, s.y^2 + d.x^2): the powers of the two real channels of a packed pair, two packed instructions
+// (ptxas folds the swap of d into an operand swizzle)
+__device__ __forceinline__ float2 pow_pair(float2 s, float2 d) {
+    float2 r;
+    asm("{.reg .b64 rs, rd, t; mov.b64 rs, {%2, %3}; mov.b64 rd, {%5, %4}; mul.rn.f32x2 t, rs, rs; fma.rn.f32x2 t, rd, rd, t; "
+        "mov.b64 {%0, %1}, t;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(s.x), "f"(s.y), "f"(d.x), "f"(d.y));
+    return r;
+}
+
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-#endif
 
 // edge frames (reflect padding, torch.stft center=True): rare, kept out of line
 template <int R1>
@@ -78,13 +84,8 @@ __device__ __forceinline__ void v3_load_raw(float2 (&v)[R1], const float* xa, co
     if ((start >= 0) && (start + F::N <= len)) {
         const float* pa = xa + start + lane;
         const float* pb = xb + start + lane;
-#ifdef SELD_ABL_NOLOAD
-#pragma unroll
-        for (int j = 0; j < R1; ++j) v[j] = make_float2(__int_as_float(0x3f000000 + j + lane + (int)start), __int_as_float(0x3e000000 + 3 * j + (int)(size_t)pb));
-#else
 #pragma unroll
         for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(pa + 32 * j), __ldg(pb + 32 * j));
-#endif
     } else {  // via a scratch array so that v itself never has its address taken (it must stay in registers)
         float2 tmp[R1];
         v3_load_edge<R1>(tmp, xa, xb, start, len, lane);
@@ -191,11 +192,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
     const long long n_gitems = (n_items + 3) >> 2;
     long long gidx = (long long)blockIdx.x * G + group;
     const long long gstride = (long long)gridDim.x * G;
-#ifdef SELD_V3_LOCKSTEP
-    if ((long long)blockIdx.x * G >= n_gitems) return;
-#else
     if (gidx >= n_gitems) return;  // whole group leaves together
-#endif
 
     const unsigned n_items_u = (unsigned)n_items, T_out_u = (unsigned)T_out;
     const long long frames_all = 1 + a.n_samples / p.hop;
@@ -239,11 +236,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
 
     while (true) {
         const long long gnext = gidx + gstride;
-#ifdef SELD_V3_LOCKSTEP
-        const bool more = gnext - group < n_gitems;  // CTA-uniform trip count; surplus items do not exist
-#else
         const bool more = gnext < n_gitems;
-#endif
         V3Ctx nxt = cur;
         if (more) nxt = make_ctx(4 * gnext + wi);
 
@@ -308,46 +301,34 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
             const bool sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
             const bool sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
 
-#ifdef SELD_ABL_NOPOST
-            if (pr < 2) {
-                float sx = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sx += u[i].x * u[i].y;
-                if (sx == 123.456f) region[lane] = sx;
-            } else
-#endif
+            // Channel split in packed form: with z = Z[k], p = conj-mirror partner Z[N-k] as shuffled (p.x, p.y),
+            // s = z + p and d = z - p (one FADD2 each) give X_a = (s.x, d.y), X_b = (s.y, -d.x)  [window pre-scaled by 1/2].
+            auto split = [&](auto KH, float2& sS, float2& dD) {
+                constexpr int kh = decltype(KH)::value;
+                const float2 z = u[kh], m = u[31 - kh];
+                float2 q;
+                q.x = __shfl_sync(0xffffffffu, m.x, src);
+                q.y = __shfl_sync(0xffffffffu, m.y, src);
+                const float2 own = u[(32 - kh) & 31];  // lane 0 holds its own mirror bins
+                q.x = lane == 0 ? own.x : q.x;
+                q.y = lane == 0 ? own.y : q.y;
+                sS = cadd(z, q);
+                dD = csub(z, q);
+            };
             if (pr == 0) {
-                // ---- park X0, X1 in planes 0..3 (read back by the same lane) ----
+                // ---- park X0 = (s.x, d.y), P1 = |X1|^2 and I1 = Re(conj(X0) X1) in planes 0..3 (same lane reads them back) ----
+                auto park = [&](int k, float2 sS, float2 dD) {
+                    region[k] = sS.x;
+                    region[L::PITCH + k] = dD.y;
+                    region[2 * L::PITCH + k] = fmaf(sS.y, sS.y, dD.x * dD.x);
+                    region[3 * L::PITCH + k] = fmaf(sS.x, sS.y, -(dD.x * dD.y));
+                };
                 static_for<16>([&](auto KH) {
-                    constexpr int kh = decltype(KH)::value;
-                    float2 x0, x1;
-                    {
-                        const float2 z = u[kh], m = u[31 - kh];
-                        float2 q;
-                        q.x = __shfl_sync(0xffffffffu, m.x, src);
-                        q.y = __shfl_sync(0xffffffffu, m.y, src);
-                        const float2 own = u[(32 - kh) & 31];
-                        q.x = lane == 0 ? own.x : q.x;
-                        q.y = lane == 0 ? own.y : q.y;
-                        F::unpack(z, q, x0, x1);
-                    }
-                    const int k = lane + R1 * kh;
-                    if (active) {  // parked in planes 0..3, read back by the same lane
-                        region[k] = x0.x;
-                        region[L::PITCH + k] = x0.y;
-                        region[2 * L::PITCH + k] = x1.x;
-                        region[3 * L::PITCH + k] = x1.y;
-                    }
+                    float2 sS, dD;
+                    split(KH, sS, dD);
+                    if (active) park(lane + R1 * decltype(KH)::value, sS, dD);
                 });
-                if (lane == 0) {
-                    float2 x0, x1;
-                    F::unpack(u[16], u[16], x0, x1);
-                    const int k = NB - 1;
-                    region[k] = x0.x;
-                    region[L::PITCH + k] = x0.y;
-                    region[2 * L::PITCH + k] = x1.x;
-                    region[3 * L::PITCH + k] = x1.y;
-                }
+                if (lane == 0) park(NB - 1, cadd(u[16], u[16]), make_float2(0.f, 0.f));
                 if (sil_a || sil_b) {  // rare: a digitally silent channel must give an exactly-zero spectrum
                     const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
                     __syncwarp();
@@ -355,60 +336,38 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
                         region[k] *= ka;
                         region[L::PITCH + k] *= ka;
                         region[2 * L::PITCH + k] *= kb;
-                        region[3 * L::PITCH + k] *= kb;
+                        region[3 * L::PITCH + k] *= ka * kb;
                     }
                     __syncwarp();
                 }
             } else {
                 // ---- per-bin features -> seven planes (planes 4..6 overlay the dead transpose tile) ----
-                static_for<16>([&](auto KH) {
-                    constexpr int kh = decltype(KH)::value;
-                    float2 x2, x3;
-                    {
-                        const float2 z = u[kh], m = u[31 - kh];
-                        float2 q;
-                        q.x = __shfl_sync(0xffffffffu, m.x, src);
-                        q.y = __shfl_sync(0xffffffffu, m.y, src);
-                        const float2 own = u[(32 - kh) & 31];
-                        q.x = lane == 0 ? own.x : q.x;
-                        q.y = lane == 0 ? own.y : q.y;
-                        F::unpack(z, q, x2, x3);
-                    }
-                    const int k = lane + R1 * kh;
-                    if (active) {
-                        const float2 x0 = make_float2(region[k], region[L::PITCH + k]);
-                        const float2 x1 = make_float2(region[2 * L::PITCH + k], region[3 * L::PITCH + k]);
-                        float4 q, r;
-                        bin_features<IV>(x0, x1, x2, x3, q, r);
-                        region[k] = q.x;
-                        region[L::PITCH + k] = q.y;
-                        region[2 * L::PITCH + k] = r.x;
-                        region[3 * L::PITCH + k] = r.y;
-                        if (IV) {
-                            region[4 * L::PITCH + k] = q.z;
-                            region[5 * L::PITCH + k] = q.w;
-                            region[6 * L::PITCH + k] = r.z;
-                        }
-                    }
-                });
-                if (lane == 0) {
-                    float2 x2, x3;
-                    F::unpack(u[16], u[16], x2, x3);
-                    const int k = NB - 1;
-                    const float2 x0 = make_float2(region[k], region[L::PITCH + k]);
-                    const float2 x1 = make_float2(region[2 * L::PITCH + k], region[3 * L::PITCH + k]);
-                    float4 q, r;
-                    bin_features<IV>(x0, x1, x2, x3, q, r);
-                    region[k] = q.x;
-                    region[L::PITCH + k] = q.y;
-                    region[2 * L::PITCH + k] = r.x;
-                    region[3 * L::PITCH + k] = r.y;
+                auto finish = [&](int k, float2 sS, float2 dD) {
+                    const float x0r = region[k], x0i = region[L::PITCH + k];
+                    const float p1 = region[2 * L::PITCH + k], i1 = region[3 * L::PITCH + k];
+                    const float2 p23 = pow_pair(sS, dD);  // (|X2|^2, |X3|^2)
+                    const float p0 = fmaf(x0r, x0r, x0i * x0i);
+                    region[k] = p0;
+                    region[L::PITCH + k] = p1;
+                    region[2 * L::PITCH + k] = p23.x;
+                    region[3 * L::PITCH + k] = p23.y;
                     if (IV) {
-                        region[4 * L::PITCH + k] = q.z;
-                        region[5 * L::PITCH + k] = q.w;
-                        region[6 * L::PITCH + k] = r.z;
+                        const float i2 = fmaf(x0r, sS.x, x0i * dD.y);     // Re(conj(X0) X2), X2 = (s.x, d.y)
+                        const float i3 = fmaf(x0r, sS.y, -(x0i * dD.x));  // Re(conj(X0) X3), X3 = (s.y, -d.x)
+                        const float e = kEpsIV + p0 + (p1 + p23.x + p23.y) * (1.0f / 3.0f);
+                        float inv;  // MUFU.RCP alone (1 ulp): e >= 1e-8 is never denormal; the IV tolerance is 1e-4 relative
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(e));
+                        region[4 * L::PITCH + k] = i1 * inv;
+                        region[5 * L::PITCH + k] = i2 * inv;
+                        region[6 * L::PITCH + k] = i3 * inv;
                     }
-                }
+                };
+                static_for<16>([&](auto KH) {
+                    float2 sS, dD;
+                    split(KH, sS, dD);
+                    if (active) finish(lane + R1 * decltype(KH)::value, sS, dD);
+                });
+                if (lane == 0) finish(NB - 1, cadd(u[16], u[16]), make_float2(0.f, 0.f));
                 if (sil_a || sil_b) {  // rare: redo the planes with the silent channel (2 = a, 3 = b) at exactly 0
                     __syncwarp();
                     for (int k = lane; k < NB; k += 32) {
@@ -442,7 +401,6 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
         group_barrier(bar_id);  // the four frames of the group are in their planes
 
         // ---- mel phase: lane = (frame, channel); this warp owns filter chunk wi ----
-#ifndef SELD_ABL_NOMEL
         {
             const int f = lane >> 3, c = lane & 7;
             const V3Meta m = s_meta[group * 4 + f];
@@ -457,7 +415,6 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
                 }
             }
         }
-#endif
         if (!more) break;
         gidx = gnext;
         cur = nxt;
