@@ -151,6 +151,84 @@ def run_reference(args):
     }))
 
 
+def run_aux(args):
+    """Secondary rows of the hot-path table: same JSON contract, N = 1, device-resident inputs.
+    mic    : configs[2], 4 log-mel + 6 GCC-PHAT x 64 lags (512 000 algorithmic bytes per clip-second)
+    logmel : the reference parity path, 4 log-mel channels (435 200 B per clip-second)
+    labels : dense (T, 648, 14) float32 grid targets, fill + paint (1 814 400 B per clip-second, write-only)"""
+    import numpy as np
+    import torch
+
+    import seld_b200
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    N = SR * CLIP_SECONDS
+    T = 1 + N // HOP
+    peak, peak_src = peaks()
+    if args.workload in ("mic", "logmel"):
+        B = args.clips
+        mode, n_out, bytes_cs = (("logmel_gcc", 10, 4 * SR * CH + 10 * N_MELS * (SR // HOP) * 4) if args.workload == "mic"
+                                 else ("logmel", 4, 4 * SR * CH + 4 * N_MELS * (SR // HOP) * 4))
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        audio = torch.empty((B, CH, N), dtype=torch.float32, device=dev).normal_(0.0, 0.1, generator=gen)
+        out = torch.empty((B, T, n_out, N_MELS), dtype=torch.float32, device=dev)
+        plan = seld_b200.get_plan(N_FFT, HOP, N_MELS, SR, dev)
+        step = lambda: plan.run(audio, mode=mode, out=out)
+        units, launches = B * CLIP_SECONDS, (2 if args.workload == "mic" else 1)
+        wl = (f"configs[2]: {B} synthetic 60 s 4-mic clips -> 4 log-mel + 6 GCC-PHAT x 64 lags" if args.workload == "mic"
+              else f"{B} synthetic 60 s 4-ch clips -> 4 log-mel channels (reference dataset.py:27-58 parity path)")
+        kernel = "seld::features_v3_kernel<32, false> + seld::gcc_phat_kernel" if args.workload == "mic" else "seld::features_v3_kernel<32, false>"
+    else:
+        from seld_b200 import labels as L
+        B = min(args.clips, 64)
+        frames = 3000
+        rng = np.random.default_rng(0)
+        ev = []
+        for b in range(B):  # 4 sources per clip, one CSV row per 100 ms each -> 5 label frames per row
+            for src in range(4):
+                f100 = np.arange(600)
+                cell = (rng.integers(0, 648) + f100 // 10) % 648
+                cls = np.full(600, rng.integers(0, 13))
+                r0 = b * frames + 5 * f100
+                ev.append(np.stack([r0, np.minimum(r0 + 5, (b + 1) * frames), cls, cell], 1))
+        ev = np.concatenate(ev).astype(np.int32)
+        out = torch.empty((B * frames, 648, 14), dtype=torch.float32, device=dev)
+        ev_d = torch.from_numpy(ev).to(dev)
+        lib, chk = seld_b200._lib.lib(), seld_b200._lib.check
+        st = torch.cuda.current_stream(dev).cuda_stream
+
+        def step():
+            chk(lib.seld_labels_fill(out.data_ptr(), out.shape[0], 648, 14, st), "fill")
+            chk(lib.seld_labels_paint(out.data_ptr(), out.shape[0], 18, 36, 14, ev_d.data_ptr(), None, len(ev), 5.0, 5.0, st), "paint")
+        units, launches, bytes_cs = B * CLIP_SECONDS, 3, 50 * 648 * 14 * 4
+        wl = f"{B} x 60 s clips -> dense (T, 648, 14) float32 grid labels (reference dataset.py:60-119), {len(ev)} events"
+        kernel = "seld::labels_fill_vec4 + seld::labels_paint_kernel (2 passes)"
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    achieved = bytes_cs * units / (ms / 1e3) / 1e9
+    print(json.dumps({
+        "metric": METRIC, "value": units / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "l2": "working set >> 126 MB L2", "timing": "CUDA events on the launch stream"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": kernel,
+                     "algorithmic_bytes_per_launch": bytes_cs * units},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": launches * args.steps, "clocks": clocks}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,9 +241,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="foa", choices=["foa", "mic", "logmel", "labels"],
+                    help="foa = BASELINE configs[1] (default, the contract line); the others are secondary rows")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "foa":
+        return run_aux(args)
 
     import torch
     import torch.distributed as dist

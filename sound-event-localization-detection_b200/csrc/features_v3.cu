@@ -293,9 +293,13 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
                 if (!active) static_for<32>([&](auto Nn) { u[decltype(Nn)::value] = make_float2(0.f, 0.f); });
             }
             __syncwarp();
-            if (pr == 0) {  // v is dead: request pair b of this frame, it lands during pass 2 and the unpacking
-                const float* xb = chan0(cur) + 2 * a.chan_stride;
-                v3_load_raw<R1>(v, xb, xb + a.chan_stride, frame_start(cur), cur.len, lane);
+            // v is dead: request the NEXT channel pair — pair b of this frame, or pair a of the group's next frame.
+            // The loads are issued here so that they interleave with the arithmetic of pass 2 and land before
+            // the next window pass (one code site for both cases).
+            if (pr == 0 || more) {
+                const V3Ctx& nx = pr == 0 ? cur : nxt;
+                const float* xn = chan0(nx) + (pr == 0 ? 2 : 0) * a.chan_stride;
+                v3_load_raw<R1>(v, xn, xn + a.chan_stride, frame_start(nx), nx.len, lane);
             }
             F::pass2(u);
             const bool sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
@@ -387,8 +391,6 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
                 }
             }
         }
-        if (more)  // request pair a of the next frame, it lands during the mel phase
-            v3_load_raw<R1>(v, chan0(nxt), chan0(nxt) + a.chan_stride, frame_start(nxt), nxt.len, lane);
         prev_valid = cur.valid;
         prev_row = cur.exists ? a.out + (((long long)cur.b * T_out + cur.t) * a.C_out + a.c_off) * 64 + 0 : nullptr;
         if (lane == 0) {
