@@ -98,6 +98,11 @@ SELD_API int seld_feature_stats(seld_plan* plan, const float* d_feat, int B, int
 SELD_API int seld_scaler_apply(float* d_x, int64_t rows, int n_feat, const float* d_mean, const float* d_inv_std,
                       void* stream);
 
+/* PCM16 ingest: d_out[i] = d_pcm[i] / 32768 (float32), the values torchaudio.load returns for a 16-bit WAV —
+ * the decode half of reference dataset.py:18-25 load_audio, done on the device so that only 2 bytes per sample
+ * cross PCIe.  Both buffers 16-byte aligned. */
+SELD_API int seld_pcm16_to_float(const int16_t* d_pcm, float* d_out, int64_t n, void* stream);
+
 /* Dense SELD grid labels (T, cells, classes) float32 for a batch of label tensors.
  * Replaces reference dataset.py:60-119 metadata_to_labels and smrl_seld_gaussian.py:397-534
  * augment_with_gaussian_noise.  The host parses the CSV exactly like the reference (pandas + int()) and

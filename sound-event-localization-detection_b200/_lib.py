@@ -32,6 +32,7 @@ _SIGS = {
     "seld_feature_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "seld_scaler_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "seld_pcm16_to_float": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "seld_labels_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "seld_labels_paint": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_double, C.c_double, C.c_void_p]),

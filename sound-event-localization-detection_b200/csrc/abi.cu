@@ -35,6 +35,7 @@ int launch_labels_paint(float* out, long long rows, int I, int J, int M, const i
 int launch_window_gather(const float* src, long long rows, long long row_len, const long long* starts, int n_win,
                          int win_len, const float* pad_row, float* out, cudaStream_t st);
 int launch_scaler_apply(float* x, long long rows, int n_feat, const float* mean, const float* inv_std, cudaStream_t st);
+int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st);
 
 }  // namespace seld
 
@@ -208,6 +209,13 @@ int seld_scaler_apply(float* d_x, int64_t rows, int n_feat, const float* d_mean,
     if (!d_x || !d_mean || !d_inv_std) return bad_arg("seld_scaler_apply: null pointer");
     if (rows < 0 || n_feat < 1) return bad_arg("seld_scaler_apply: bad size");
     return launch_scaler_apply(d_x, rows, n_feat, d_mean, d_inv_std, static_cast<cudaStream_t>(stream));
+}
+
+int seld_pcm16_to_float(const int16_t* d_pcm, float* d_out, int64_t n, void* stream) {
+    if (n < 0) return bad_arg("seld_pcm16_to_float: negative size");
+    if (n == 0) return SELD_OK;
+    if (!d_pcm || !d_out) return bad_arg("seld_pcm16_to_float: null pointer");
+    return launch_pcm16_to_float(d_pcm, d_out, n, static_cast<cudaStream_t>(stream));
 }
 
 int seld_labels_fill(float* d_out, int64_t rows, int cells, int n_classes, void* stream) {

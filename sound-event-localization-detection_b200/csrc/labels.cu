@@ -192,4 +192,38 @@ int launch_scaler_apply(float* x, long long rows, int n_feat, const float* mean,
     return SELD_OK;
 }
 
+// ---- PCM16 ingest: int16 samples -> float32 in [-1, 1), x / 32768 (what torchaudio.load returns for 16-bit WAV, the
+// input of reference dataset.py:18-25 load_audio).  Uploading int16 and converting here halves the PCIe bytes. ----
+__global__ void pcm16_to_float_kernel(const short* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n8 = n / 8;
+    const uint4* in8 = reinterpret_cast<const uint4*>(in);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    constexpr float k = 1.0f / 32768.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const uint4 v = __ldg(in8 + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[2 * j] = k * (float)(short)(w[j] & 0xffffu);
+            f[2 * j + 1] = k * (float)(short)(w[j] >> 16);
+        }
+        __stcs(out4 + 2 * i, make_float4(f[0], f[1], f[2], f[3]));
+        __stcs(out4 + 2 * i + 1, make_float4(f[4], f[5], f[6], f[7]));
+    }
+    for (long long i = 8 * n8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = k * (float)in[i];
+}
+
+int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st) {
+    if (n == 0) return SELD_OK;
+    if (!aligned16(in) || !aligned16(out)) {
+        set_error("seld_pcm16_to_float: buffers must be 16-byte aligned");
+        return SELD_ERR_BAD_ARG;
+    }
+    pcm16_to_float_kernel<<<grid_for((n + 7) / 8, 256, current_sms()), 256, 0, st>>>(in, out, n);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
 }  // namespace seld

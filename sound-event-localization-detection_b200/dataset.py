@@ -243,6 +243,16 @@ class SELDDataset(Dataset):
         return window['spectrogram'], window['labels']
 
     # ------------------------------------------------------------------------------------------
+    def _events_sorted(self):
+        """Event table sorted by first row (stable), built once; painting order inside a window does not matter
+        (the paint kernel's two passes are order-independent)."""
+        if getattr(self, "_ev_sorted", None) is None:
+            ev, ce = self.events, self.centres
+            order = np.argsort(ev[:, 0], kind="stable") if len(ev) else np.zeros(0, np.int64)
+            self._ev_sorted = (np.ascontiguousarray(ev[order]), None if ce is None else np.ascontiguousarray(ce[order]))
+            self._ev_maxlen = int((ev[:, 1] - ev[:, 0]).max()) if len(ev) else 1
+        return self._ev_sorted
+
     def paint_label_windows(self, starts, out: torch.Tensor | None = None) -> torch.Tensor:
         """Dense labels (n, W, I*J, M) for windows starting at ``starts``, painted on the GPU from the compact
         event tables (background for frames past the end, like the reference's padding)."""
@@ -250,18 +260,23 @@ class SELDDataset(Dataset):
         n = len(starts)
         if out is None:
             out = torch.empty((n, W, self.total_cells, self.num_classes), dtype=torch.float32, device=self.device)
-        ev_all, ce_all = self.events, self.centres
+        ev_all, ce_all = self._events_sorted()
         evs, ces = [], []
-        for w, s in enumerate(starts):
-            if len(ev_all) == 0:
-                continue
-            sel = (ev_all[:, 1] > s) & (ev_all[:, 0] < min(s + W, T))
-            e = ev_all[sel].copy()
-            e[:, 0] = np.maximum(e[:, 0], s) - s + w * W
-            e[:, 1] = np.minimum(e[:, 1], s + W) - s + w * W
-            evs.append(e)
-            if ce_all is not None:
-                ces.append(ce_all[sel])
+        if len(ev_all):
+            # events are sorted by first row and last at most _ev_maxlen rows: a window only needs a binary search
+            row0 = ev_all[:, 0]
+            s_arr = np.asarray(starts, dtype=np.int64)
+            lo = np.searchsorted(row0, s_arr - (self._ev_maxlen - 1), side="left")
+            hi = np.searchsorted(row0, np.minimum(s_arr + W, T), side="left")
+            for w, s in enumerate(starts):
+                e = ev_all[lo[w]:hi[w]]
+                sel = e[:, 1] > s
+                e = e[sel].copy()
+                e[:, 0] = np.maximum(e[:, 0], s) - s + w * W
+                e[:, 1] = np.minimum(e[:, 1], s + W) - s + w * W
+                evs.append(e)
+                if ce_all is not None:
+                    ces.append(ce_all[lo[w]:hi[w]][sel])
         events = np.concatenate(evs) if evs else np.zeros((0, 4), np.int32)
         centres = np.concatenate(ces) if ces else None
         L.encode_dense(out.view(n * W, self.total_cells, self.num_classes), events, centres, self.I, self.J)

@@ -189,37 +189,48 @@ def audio_to_mel_spectrogram(waveform: torch.Tensor, sample_rate: int, n_fft=Non
 
 def extract_features_host(audio_host: torch.Tensor, out_host: torch.Tensor, plan: FeaturePlan, mode="logmel",
                           chunk: int = 16, n_streams: int = 3) -> torch.Tensor:
-    """End-to-end path for HOST buffers: (B, C, N) float32 (ideally pinned) -> out_host (B, T, C_out, n_mels).
+    """End-to-end path for HOST buffers: (B, C, N) float32 — or int16 PCM, converted on the device as x / 32768 like
+    torchaudio.load does for 16-bit WAV (reference dataset.py:18-25) — (ideally pinned) -> out_host
+    (B, T, C_out, n_mels).
 
     Clips are streamed through the GPU in chunks on ``n_streams`` CUDA streams so that the host->device
     copy of chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap (PCIe is full
     duplex).  Returns when the features are in ``out_host``."""
     if audio_host.is_cuda or out_host.is_cuda:
         raise ValueError("extract_features_host takes host tensors; use FeaturePlan.run for device tensors")
+    if audio_host.dtype not in (torch.float32, torch.int16):
+        raise ValueError("audio_host must be float32 or int16 (PCM16)")
+    pcm = audio_host.dtype == torch.int16
     B, Cn, N = audio_host.shape
     T = plan.num_frames(N)
     m = MODES[mode] if isinstance(mode, str) else int(mode)
     n_out = plan.out_channels(m, Cn)
     if tuple(out_host.shape) != (B, T, n_out, plan.n_mels) or out_host.dtype != torch.float32:
         raise ValueError(f"out_host must be float32 {(B, T, n_out, plan.n_mels)}")
-    key = (chunk, Cn, N, n_out, n_streams)
+    key = (chunk, Cn, N, n_out, n_streams, pcm)
     cache = plan.__dict__.setdefault("_host_pipes", {})
     pipe = cache.get(key)
     if pipe is None:
         pipe = cache[key] = [(torch.cuda.Stream(plan.device),
                               torch.empty((chunk, Cn, N), dtype=torch.float32, device=plan.device),
-                              torch.empty((chunk, T, n_out, plan.n_mels), dtype=torch.float32, device=plan.device))
+                              torch.empty((chunk, T, n_out, plan.n_mels), dtype=torch.float32, device=plan.device),
+                              torch.empty((chunk, Cn, N), dtype=torch.int16, device=plan.device) if pcm else None)
                              for _ in range(n_streams)]
     cur = torch.cuda.current_stream(plan.device)
-    for s, _, _ in pipe:
+    for s, *_ in pipe:
         s.wait_stream(cur)
     for i, b0 in enumerate(range(0, B, chunk)):
-        s, d_in, d_out = pipe[i % n_streams]
+        s, d_in, d_out, d_pcm = pipe[i % n_streams]
         nb = min(chunk, B - b0)
         with torch.cuda.stream(s):
-            d_in[:nb].copy_(audio_host[b0:b0 + nb], non_blocking=True)
+            if pcm:
+                d_pcm[:nb].copy_(audio_host[b0:b0 + nb], non_blocking=True)
+                _lib.check(_lib.lib().seld_pcm16_to_float(d_pcm.data_ptr(), d_in.data_ptr(), nb * Cn * N, s.cuda_stream),
+                           "seld_pcm16_to_float")
+            else:
+                d_in[:nb].copy_(audio_host[b0:b0 + nb], non_blocking=True)
             plan.run(d_in[:nb], mode=m, out=d_out[:nb])
             out_host[b0:b0 + nb].copy_(d_out[:nb], non_blocking=True)
-    for s, _, _ in pipe:
+    for s, *_ in pipe:
         s.synchronize()
     return out_host

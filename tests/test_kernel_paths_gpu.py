@@ -129,3 +129,17 @@ def test_feature_stats_call_matches_fused_accumulation(sb):
     rows = np.concatenate([out[0, :T - 1].cpu(), out[1, :T].cpu(), out[2, :10].cpu()]).astype(np.float64).reshape(-1, 448)
     assert np.allclose(s2.cpu().numpy()[:448], rows.sum(0), rtol=1e-9, atol=1e-6)
     assert np.allclose(s2.cpu().numpy()[448:], (rows * rows).sum(0), rtol=1e-9, atol=1e-6)
+
+
+def test_pcm16_host_path_matches_float_path(sb):
+    """int16 PCM host input (x / 32768 on the device, like torchaudio.load for 16-bit WAV) == float32 host input."""
+    from seld_b200.features import extract_features_host
+    rng = np.random.default_rng(11)
+    pcm = rng.integers(-20000, 20000, size=(5, 4, 24000 + 77), dtype=np.int16)
+    plan = sb.get_plan(1024, 480, 64, 24000, "cuda")
+    T = 1 + pcm.shape[2] // 480
+    out_f = torch.empty((5, T, 7, 64), dtype=torch.float32).pin_memory()
+    out_i = torch.empty_like(out_f).pin_memory()
+    extract_features_host(torch.from_numpy(pcm.astype(np.float32) / 32768.0).pin_memory(), out_f, plan, mode="logmel_iv", chunk=2)
+    extract_features_host(torch.from_numpy(pcm).pin_memory(), out_i, plan, mode="logmel_iv", chunk=2)
+    assert torch.equal(out_f, out_i)
