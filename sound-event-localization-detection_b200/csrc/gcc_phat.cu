@@ -13,20 +13,32 @@ namespace seld {
 
 constexpr int kGccWarps = 8;  // per-warp shared memory: two phasor stashes + transpose tile (24.9 KB)
 
+// edge frames (reflect padding): rare, kept out of line so the interior path is 64 plain loads
+template <int R1>
+__device__ __noinline__ void gcc_load_edge(float2 (&v)[R1], const float* xa, const float* xb, long long start,
+                                           long long len, int lane) {
+    using F = WarpFft<R1>;
+#pragma unroll 4
+    for (int j = 0; j < R1; ++j) {
+        const long long idx = F::reflect(start + lane + 32 * j, len);
+        v[j] = make_float2(__ldg(xa + idx), __ldg(xb + idx));
+    }
+}
+
 template <int R1>
 __device__ __forceinline__ void gcc_load_raw(float2 (&v)[R1], const float* xa, const float* xb, long long start,
                                              long long len, int lane) {
     using F = WarpFft<R1>;
-    const bool interior = (start >= 0) && (start + F::N <= len);
-    if (interior) {
+    if ((start >= 0) && (start + F::N <= len)) {
+        const float* pa = xa + start + lane;
+        const float* pb = xb + start + lane;
 #pragma unroll
-        for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(xa + start + lane + 32 * j), __ldg(xb + start + lane + 32 * j));
-    } else {
+        for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(pa + 32 * j), __ldg(pb + 32 * j));
+    } else {  // via a scratch array so that v itself never has its address taken
+        float2 tmp[R1];
+        gcc_load_edge<R1>(tmp, xa, xb, start, len, lane);
 #pragma unroll
-        for (int j = 0; j < R1; ++j) {
-            const long long idx = F::reflect(start + lane + 32 * j, len);
-            v[j] = make_float2(__ldg(xa + idx), __ldg(xb + idx));
-        }
+        for (int j = 0; j < R1; ++j) v[j] = tmp[j];
     }
 }
 
@@ -38,8 +50,9 @@ __device__ __forceinline__ float2 unit_phasor(float2 x) {
 // conj(a) * b for unit (or zero) phasors; a zero operand means R == 0 -> exp(j*angle(0)) = 1
 __device__ __forceinline__ float2 phat(float2 a, float2 b) {
     float2 g = make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
-    const bool zero = (a.x == 0.f && a.y == 0.f) || (b.x == 0.f && b.y == 0.f);
-    return zero ? make_float2(1.f, 0.f) : g;
+    // unit phasors have |g| ~ 1; g is exactly (0, 0) iff one operand is the zero phasor -> only g.x needs patching
+    g.x = (g.x == 0.f && g.y == 0.f) ? 1.f : g.x;
+    return g;
 }
 
 template <int PP>
@@ -92,9 +105,7 @@ __global__ void __launch_bounds__(kGccWarps * 32, 1) gcc_phat_kernel(PlanDev p, 
                 F::silent_channels(v, sil_a, sil_b);
 #pragma unroll
                 for (int j = 0; j < R1; ++j) {
-                    const float w = s_win[lane + 32 * j];
-                    v[j].x *= w;
-                    v[j].y *= w;
+                    v[j] = cscale(v[j], s_win[lane + 32 * j]);
                 }
                 F::pass1(v, s_tw + lane);
                 __syncwarp();
