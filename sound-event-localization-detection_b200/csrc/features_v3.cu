@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
     const long long gstride = (long long)gridDim.x * G;
     if (gidx >= n_gitems) return;  // whole group leaves together
 
-    const unsigned n_items_u = (unsigned)n_items, T_out_u = (unsigned)T_out;
+    const unsigned T_out_u = (unsigned)T_out;
     const long long frames_all = 1 + a.n_samples / p.hop;
     auto make_ctx = [&](long long item) {
         V3Ctx c;
