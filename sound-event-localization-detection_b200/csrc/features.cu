@@ -385,17 +385,9 @@ static int launch_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t str
     return SELD_OK;
 }
 
-// warps per CTA: 12 fills the 227 KB of shared memory (168 registers/thread); SELD_FEAT_WARPS=8|10 trades
-// occupancy for registers and L1 (tuning knob, read once)
+// 12 warps per CTA fill the 227 KB of shared memory (168 registers per thread)
 template <int R1, bool IV, bool SPEC>
 static int launch_w(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    static const int warps = [] {
-        const char* e = getenv("SELD_FEAT_WARPS");
-        const int w = e ? atoi(e) : kFeatWarps;
-        return (w == 8 || w == 10) ? w : kFeatWarps;
-    }();
-    if (!SPEC && warps == 10) return launch_one<R1, IV, SPEC, 10>(plan, a, stream);
-    if (!SPEC && warps == 8) return launch_one<R1, IV, SPEC, 8>(plan, a, stream);
     return launch_one<R1, IV, SPEC, kFeatWarps>(plan, a, stream);
 }
 
