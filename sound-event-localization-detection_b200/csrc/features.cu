@@ -372,6 +372,58 @@ __global__ void __launch_bounds__(512) feature_stats_kernel(const float* __restr
     }
 }
 
+// 128-bit variant: a thread owns 4 adjacent columns and every 8th row of a 128-row slab, 8 loads of 16 bytes in
+// flight per thread (the scalar kernel above keeps too few bytes in flight to fill HBM).
+constexpr int kStatRows4 = 128;
+__global__ void __launch_bounds__(1024) feature_stats_kernel_v4(const float* __restrict__ x, long long T_out, int F,
+                                                                int col0, int ncols4, int B, const int* __restrict__ frames,
+                                                                const long long* __restrict__ lengths, long long n_samples,
+                                                                int hop, double* __restrict__ stats) {
+    extern __shared__ double s_part[];  // [8][ncols4][8]
+    __shared__ unsigned char s_valid[kStatRows4];
+    const long long total_rows = (long long)B * T_out;
+    const long long r0 = (long long)blockIdx.x * kStatRows4;
+    const int n_rows = (int)min((long long)kStatRows4, total_rows - r0);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < kStatRows4) {
+        bool ok = false;
+        if (tid < n_rows) {
+            const long long r = r0 + tid, b = r / T_out, t = r - b * T_out;
+            const long long lim = frames ? (long long)frames[b] : 1 + (lengths ? lengths[b] : n_samples) / hop;
+            ok = t < lim;
+        }
+        s_valid[tid] = ok;
+    }
+    __syncthreads();
+    const int j = threadIdx.x;  // column quad
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (j < ncols4) {
+        const float4* px = reinterpret_cast<const float4*>(x + r0 * F + col0) + j;
+        const int F4 = F / 4;
+#pragma unroll 8
+        for (int r = threadIdx.y; r < n_rows; r += 8) {
+            float4 v = __ldg(px + (long long)r * F4);
+            if (!s_valid[r]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const double a0 = v.x, a1 = v.y, a2 = v.z, a3 = v.w;
+            acc[0] += a0; acc[1] += a1; acc[2] += a2; acc[3] += a3;
+            acc[4] = fma(a0, a0, acc[4]); acc[5] = fma(a1, a1, acc[5]);
+            acc[6] = fma(a2, a2, acc[6]); acc[7] = fma(a3, a3, acc[7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[(threadIdx.y * ncols4 + j) * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && j < ncols4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) t += s_part[(y * ncols4 + j) * 8 + i];
+            atomicAdd(stats + (i < 4 ? 0 : F) + col0 + 4 * j + (i & 3), t);
+        }
+    }
+}
+
 template <int R1, bool IV, bool SPEC, int WARPS>
 static int launch_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
     auto kern = features_kernel<R1, IV, SPEC, WARPS>;
@@ -396,6 +448,19 @@ int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t 
     const long long rows = (long long)a.B * a.T_out;
     const int ncols = a.n_out * plan->dev.n_mels;
     if (rows < 1 || ncols < 1) return SELD_OK;
+    const int col0 = a.c_off * plan->dev.n_mels;
+    if (F % 4 == 0 && col0 % 4 == 0 && ncols % 4 == 0 && ncols / 4 <= 128 &&
+        (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
+        const int ncols4 = ncols / 4;
+        dim3 grid4((unsigned)((rows + kStatRows4 - 1) / kStatRows4)), block4((unsigned)((ncols4 + 31) / 32 * 32), 8);
+        const size_t smem = sizeof(double) * 8 * ncols4 * 8;
+        if (smem > 48 * 1024)
+            SELD_CUDA_TRY(cudaFuncSetAttribute(feature_stats_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_stats_kernel_v4<<<grid4, block4, smem, stream>>>(a.out, a.T_out, F, col0, ncols4, a.B, a.stat_frames,
+                                                                  a.lengths, a.n_samples, plan->dev.hop, a.stats);
+        SELD_CUDA_TRY(cudaGetLastError());
+        return SELD_OK;
+    }
     dim3 grid((unsigned)((rows + kStatRows - 1) / kStatRows), (unsigned)((ncols + 63) / 64)), block(64, 8);
     feature_stats_kernel<<<grid, block, 0, stream>>>(a.out, a.T_out, F, a.c_off * plan->dev.n_mels, ncols, a.B,
                                                      a.stat_frames, a.lengths, a.n_samples, plan->dev.hop, a.stats);
