@@ -16,15 +16,16 @@
 //     the instruction stream (mel_baked.h: weights are FFMA immediates, filter boundaries are straight-line
 //     code), every plane word is read exactly once (no gather tables, no padding, no bank conflicts) and
 //     each warp owns a quarter of the filters.  Results go to global memory as 16-byte stores.
+#include <cstdlib>
+
 #include "mel_baked.h"
 #include "seld_common.h"
 #include "warp_fft.cuh"
 
 namespace seld {
 
-constexpr int kV3Warps = 12;  // 3 groups of 4 warps; 1 CTA per SM (shared-memory bound)
 
-template <int R1>
+template <int R1, bool REGSTASH>
 struct V3Layout {
     using F = WarpFft<R1>;
     static constexpr int NB = F::NB;                         // 513 / 481
@@ -38,7 +39,8 @@ struct V3Layout {
     // 9 x 16 B and 17 x 16 B put the 8 lanes of a quarter-warp on 8 different 16-byte bank groups
     static constexpr int WIN_PITCH = 36;                     // floats:  window[lane + 32 j] / 2 at [lane][j]
     static constexpr int TW_PITCH = 34;                      // float2s: W_N^(lane k) at [lane][k]
-    static constexpr int REGION = TILE_OFF + TILE_WORDS;     // >= 7 planes
+    static constexpr int OUT_END = 7 * PITCH + 31 + 7 * 65;
+    static constexpr int REGION = ((TILE_OFF + TILE_WORDS > OUT_END ? TILE_OFF + TILE_WORDS : OUT_END) + 3) & ~3;
     // behind the seven planes: the frame's finished output row (7 x 64, channel pitch 65), staged by the mel phase
     // and copied out as full 128-byte lines by the owning warp.  Frame slot f starts at OUT_OFF + out_skew(f)
     // so that lane (f, c) lands on bank 8 f + c + m.
@@ -155,17 +157,17 @@ struct V3Ctx {        // one frame: clip b, frame t
     int valid, exists;
 };
 
-template <int R1, bool IV>
-__global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p, FeatArgs a) {
+template <int R1, bool IV, int WARPS, bool REGSTASH>
+__global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, FeatArgs a) {
     using F = WarpFft<R1>;
-    using L = V3Layout<R1>;
+    using L = V3Layout<R1, REGSTASH>;
     constexpr int N = F::N, NB = F::NB;
     constexpr int NCH = IV ? 7 : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * L::WIN_PITCH);
     V3Meta* s_meta = reinterpret_cast<V3Meta*>(s_tw + 32 * L::TW_PITCH);
-    float* s_regions = reinterpret_cast<float*>(s_meta + kV3Warps);
+    float* s_regions = reinterpret_cast<float*>(s_meta + WARPS);
 
     for (int i = threadIdx.x; i < 32 * L::WIN_PITCH; i += blockDim.x) {
         const int l = i / L::WIN_PITCH, j = i - l * L::WIN_PITCH;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
     const int src = F::partner_lane(lane);
     const bool active = R1 == 32 || lane < R1;
     const int bar_id = 1 + group;
-    constexpr int G = kV3Warps / 4;
+    constexpr int G = WARPS / 4;
 
     const long long n_items = a.n_items, T_out = a.T_out;
     const long long n_gitems = (n_items + 3) >> 2;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
         V3Ctx nxt = cur;
         if (more) nxt = make_ctx(4 * gnext + wi);
 
+        float4 st[REGSTASH ? 17 : 1];  // REGSTASH: (X0.re, X0.im, P1, I1) of the lane's 17 bins while pair b is transformed
 #pragma unroll 1
         for (int pr = 0; pr < 2; ++pr) {
             // ---- window + pass 1 + twiddle (registers only) ----
@@ -321,19 +324,30 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
             };
             if (pr == 0) {
                 // ---- park X0 = (s.x, d.y), P1 = |X1|^2 and I1 = Re(conj(X0) X1) in planes 0..3 (same lane reads them back) ----
-                auto park = [&](int k, float2 sS, float2 dD) {
-                    region[k] = sS.x;
-                    region[L::PITCH + k] = dD.y;
-                    region[2 * L::PITCH + k] = fmaf(sS.y, sS.y, dD.x * dD.x);
-                    region[3 * L::PITCH + k] = fmaf(sS.x, sS.y, -(dD.x * dD.y));
+                auto park = [&](auto Slot, int k, float2 sS, float2 dD) {
+                    const float p1 = fmaf(sS.y, sS.y, dD.x * dD.x), i1 = fmaf(sS.x, sS.y, -(dD.x * dD.y));
+                    if constexpr (REGSTASH) {
+                        st[decltype(Slot)::value] = make_float4(sS.x, dD.y, p1, i1);
+                    } else {
+                        region[k] = sS.x;
+                        region[L::PITCH + k] = dD.y;
+                        region[2 * L::PITCH + k] = p1;
+                        region[3 * L::PITCH + k] = i1;
+                    }
                 };
                 static_for<16>([&](auto KH) {
                     float2 sS, dD;
                     split(KH, sS, dD);
-                    if (active) park(lane + R1 * decltype(KH)::value, sS, dD);
+                    if (REGSTASH || active) park(KH, lane + R1 * decltype(KH)::value, sS, dD);
                 });
-                if (lane == 0) park(NB - 1, cadd(u[16], u[16]), make_float2(0.f, 0.f));
-                if (sil_a || sil_b) {  // rare: a digitally silent channel must give an exactly-zero spectrum
+                if (REGSTASH || lane == 0) park(std::integral_constant<int, REGSTASH ? 16 : 0>{}, NB - 1, cadd(u[16], u[16]), make_float2(0.f, 0.f));
+                if constexpr (REGSTASH) {
+                    if (sil_a || sil_b) {  // rare: a digitally silent channel must give an exactly-zero spectrum
+                        const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
+#pragma unroll
+                        for (int i = 0; i < 17; ++i) st[i] = make_float4(st[i].x * ka, st[i].y * ka, st[i].z * kb, st[i].w * ka * kb);
+                    }
+                } else if (sil_a || sil_b) {  // rare: a digitally silent channel must give an exactly-zero spectrum
                     const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
                     __syncwarp();
                     for (int k = lane; k < NB; k += 32) {
@@ -346,9 +360,15 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
                 }
             } else {
                 // ---- per-bin features -> seven planes (planes 4..6 overlay the dead transpose tile) ----
-                auto finish = [&](int k, float2 sS, float2 dD) {
-                    const float x0r = region[k], x0i = region[L::PITCH + k];
-                    const float p1 = region[2 * L::PITCH + k], i1 = region[3 * L::PITCH + k];
+                auto finish = [&](auto Slot, int k, float2 sS, float2 dD) {
+                    float x0r, x0i, p1, i1;
+                    if constexpr (REGSTASH) {
+                        const float4 t = st[decltype(Slot)::value];
+                        x0r = t.x, x0i = t.y, p1 = t.z, i1 = t.w;
+                    } else {
+                        x0r = region[k], x0i = region[L::PITCH + k];
+                        p1 = region[2 * L::PITCH + k], i1 = region[3 * L::PITCH + k];
+                    }
                     const float2 p23 = pow_pair(sS, dD);  // (|X2|^2, |X3|^2)
                     const float p0 = fmaf(x0r, x0r, x0i * x0i);
                     region[k] = p0;
@@ -369,9 +389,9 @@ __global__ void __launch_bounds__(kV3Warps * 32, 1) features_v3_kernel(PlanDev p
                 static_for<16>([&](auto KH) {
                     float2 sS, dD;
                     split(KH, sS, dD);
-                    if (active) finish(lane + R1 * decltype(KH)::value, sS, dD);
+                    if (active) finish(KH, lane + R1 * decltype(KH)::value, sS, dD);
                 });
-                if (lane == 0) finish(NB - 1, cadd(u[16], u[16]), make_float2(0.f, 0.f));
+                if (lane == 0) finish(std::integral_constant<int, REGSTASH ? 16 : 0>{}, NB - 1, cadd(u[16], u[16]), make_float2(0.f, 0.f));
                 if (sil_a || sil_b) {  // rare: redo the planes with the silent channel (2 = a, 3 = b) at exactly 0
                     __syncwarp();
                     for (int k = lane; k < NB; k += 32) {
@@ -443,20 +463,30 @@ bool v3_filterbank_matches(int n_fft, const float* fb, int n_mels) {
     return n_fft == 1024 ? fb_matches<1024>(fb, n_mels) : n_fft == 960 ? fb_matches<960>(fb, n_mels) : false;
 }
 
-template <int R1, bool IV>
-static int launch_v3_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    using L = V3Layout<R1>;
-    auto kern = features_v3_kernel<R1, IV>;
-    const size_t smem = sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH) + sizeof(V3Meta) * kV3Warps +
-                        sizeof(float) * (size_t)kV3Warps * L::REGION;
+template <int R1, bool IV, int WARPS, bool REGSTASH>
+static int launch_v3_cfg(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
+    using L = V3Layout<R1, REGSTASH>;
+    auto kern = features_v3_kernel<R1, IV, WARPS, REGSTASH>;
+    const size_t smem = sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH) + sizeof(V3Meta) * WARPS +
+                        sizeof(float) * (size_t)WARPS * L::REGION;
     SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_gitems = (a.n_items + 3) / 4;
-    long long ctas = (n_gitems + kV3Warps / 4 - 1) / (kV3Warps / 4);
+    long long ctas = (n_gitems + WARPS / 4 - 1) / (WARPS / 4);
     if (ctas > plan->num_sms) ctas = plan->num_sms;
     if (ctas < 1) return SELD_OK;
-    kern<<<(unsigned)ctas, kV3Warps * 32, smem, stream>>>(plan->dev, a);
+    kern<<<(unsigned)ctas, WARPS * 32, smem, stream>>>(plan->dev, a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
+}
+
+// Two resource configurations of the same kernel (SELD_V3_CFG=12s|8r selects one for A/B runs):
+//   12s: 12 warps x 168 registers, first pair's spectra parked in shared memory
+//   8r :  8 warps x 255 registers, parked in registers (136 fewer shared-memory wavefronts per frame, more L1)
+template <int R1, bool IV>
+static int launch_v3_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
+    const char* e = getenv("SELD_V3_CFG");  // measured equal at n_fft 1024 (4.45 vs 4.47 ms), 12s faster at 960
+    if (e && e[0] == '8') return launch_v3_cfg<R1, IV, 8, true>(plan, a, stream);
+    return launch_v3_cfg<R1, IV, 12, false>(plan, a, stream);
 }
 
 int launch_features_v3(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream) {
