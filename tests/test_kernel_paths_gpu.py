@@ -143,3 +143,30 @@ def test_pcm16_host_path_matches_float_path(sb):
     extract_features_host(torch.from_numpy(pcm.astype(np.float32) / 32768.0).pin_memory(), out_f, plan, mode="logmel_iv", chunk=2)
     extract_features_host(torch.from_numpy(pcm).pin_memory(), out_i, plan, mode="logmel_iv", chunk=2)
     assert torch.equal(out_f, out_i)
+
+
+def test_v3_is_deterministic_and_configuration_independent(sb):
+    """The two resource configurations of the v3 kernel (12 warps / spectra parked in shared memory, 8 warps / parked
+    in registers) run the same arithmetic in the same order: bit-identical outputs, run after run.  (This is also the
+    shared-memory race check: the in-place planes, the tile overlay and the staged rows would show up as differences.)"""
+    g = torch.Generator().manual_seed(7)
+    x = (0.1 * torch.randn(6, 4, 24000 * 20 + 333, generator=g)).cuda()
+    outs = []
+    old = os.environ.get("SELD_V3_CFG")
+    try:
+        for cfg in ("12s", "8r", "12s", "8r"):
+            os.environ["SELD_V3_CFG"] = cfg
+            outs.append(sb.extract_features(x, 24000, 1024, 480, 64, mode="logmel_iv").clone())
+        os.environ["SELD_V3_CFG"] = "12s"
+        o960 = [sb.extract_features(x, 24000, 960, 480, 64, mode="logmel_iv").clone() for _ in range(2)]
+        os.environ["SELD_V3_CFG"] = "8r"
+        o960.append(sb.extract_features(x, 24000, 960, 480, 64, mode="logmel_iv").clone())
+    finally:
+        if old is None:
+            os.environ.pop("SELD_V3_CFG", None)
+        else:
+            os.environ["SELD_V3_CFG"] = old
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+    for o in o960[1:]:
+        assert torch.equal(o960[0], o)
