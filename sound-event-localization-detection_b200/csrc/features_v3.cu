@@ -246,7 +246,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
 #pragma unroll 1
         for (int pr = 0; pr < 2; ++pr) {
             // ---- window + pass 1 + twiddle (registers only) ----
-            unsigned bits_a = 0u, bits_b = 0u;
+            // Digitally silent channel?  Cheap necessary test first (every lane's first sample is +-0); the OR over all
+            // raw samples only runs when it passes (rare, warp-uniform).
+            bool sil_a = !__any_sync(0xffffffffu, (__float_as_uint(v[0].x) << 1) != 0u);
+            bool sil_b = !__any_sync(0xffffffffu, (__float_as_uint(v[0].y) << 1) != 0u);
+            if (sil_a || sil_b) {
+                unsigned bits_a = 0u, bits_b = 0u;
+#pragma unroll
+                for (int j = 0; j < R1; ++j) {
+                    bits_a |= __float_as_uint(v[j].x);
+                    bits_b |= __float_as_uint(v[j].y);
+                }
+                sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
+                sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
+            }
             {
                 const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * L::WIN_PITCH);
                 static_for<(R1 + 3) / 4>([&](auto Jq) {
@@ -256,8 +269,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
                         constexpr int j = j0 + decltype(Ji)::value;
                         if constexpr (j < R1) {
                             const float w = decltype(Ji)::value == 0 ? w4.x : decltype(Ji)::value == 1 ? w4.y : decltype(Ji)::value == 2 ? w4.z : w4.w;
-                            bits_a |= __float_as_uint(v[j].x);
-                            bits_b |= __float_as_uint(v[j].y);
                             v[j] = cscale(v[j], w);
                         }
                     });
@@ -305,8 +316,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
                 v3_load_raw<R1>(v, xn, xn + a.chan_stride, frame_start(nx), nx.len, lane);
             }
             F::pass2(u);
-            const bool sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
-            const bool sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
 
             // Channel split in packed form: with z = Z[k], p = conj-mirror partner Z[N-k] as shuffled (p.x, p.y),
             // s = z + p and d = z - p (one FADD2 each) give X_a = (s.x, d.y), X_b = (s.y, -d.x)  [window pre-scaled by 1/2].
