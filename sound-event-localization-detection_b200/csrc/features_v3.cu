@@ -246,6 +246,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
 #pragma unroll 1
         for (int pr = 0; pr < 2; ++pr) {
             // ---- window + pass 1 + twiddle (registers only) ----
+            // the other warps of the group have finished reading this region (previous mel phase); the previous
+            // frame's row is complete (all four filter chunks staged): its copy-out overlaps the first pass below
+            if (pr == 0) {
+                group_barrier(bar_id);
+                copy_out();
+            }
             // Digitally silent channel?  Cheap necessary test first (every lane's first sample is +-0); the OR over all
             // raw samples only runs when it passes (rare, warp-uniform).
             bool sil_a = !__any_sync(0xffffffffu, (__float_as_uint(v[0].x) << 1) != 0u);
@@ -283,11 +289,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
                     if constexpr (k0 >= 1) v[k0] = cmul(v[k0], make_float2(t4.x, t4.y));
                     if constexpr (k0 + 1 < R1) v[k0 + 1] = cmul(v[k0 + 1], make_float2(t4.z, t4.w));
                 });
-            }
-            // the other warps of the group have finished reading this region (previous mel phase)
-            if (pr == 0) {
-                group_barrier(bar_id);
-                copy_out();  // the previous frame's row is complete (all four filter chunks staged)
             }
             __syncwarp();
             static_for<R1>([&](auto K) {  // row k belongs to reader lane k; column = this lane
