@@ -246,6 +246,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
 #pragma unroll 1
         for (int pr = 0; pr < 2; ++pr) {
             // ---- window + pass 1 + twiddle (registers only) ----
+            // this lane's window row (a constant table: fetched before the barrier so that the loads are in flight)
+            float4 wreg[(R1 + 3) / 4];
+            {
+                const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * L::WIN_PITCH);
+#pragma unroll
+                for (int i = 0; i < (R1 + 3) / 4; ++i) wreg[i] = wrow[i];
+            }
             // the other warps of the group have finished reading this region (previous mel phase); the previous
             // frame's row is complete (all four filter chunks staged): its copy-out overlaps the first pass below
             if (pr == 0) {
@@ -267,10 +274,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
                 sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
             }
             {
-                const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * L::WIN_PITCH);
                 static_for<(R1 + 3) / 4>([&](auto Jq) {
                     constexpr int j0 = 4 * decltype(Jq)::value;
-                    const float4 w4 = wrow[j0 / 4];
+                    const float4 w4 = wreg[j0 / 4];
                     static_for<4>([&](auto Ji) {
                         constexpr int j = j0 + decltype(Ji)::value;
                         if constexpr (j < R1) {
