@@ -49,11 +49,6 @@ struct V3Layout {
     static_assert(PITCH % 8 == 4 && REGION % 4 == 0 && REGION >= OUT_OFF + 31 + 7 * OUT_PITCH, "region layout");
 };
 
-struct V3Meta {       // per frame slot of a group, written by the owning warp before the barrier
-    float* out_row;   // out[b, t, c_off, 0]
-    int valid;        // t < frames of the clip (else the row is written as 0)
-    int write;        // the item exists at all
-};
 
 // (s.x^2 + d.y^2, s.y^2 + d.x^2): the powers of the two real channels of a packed pair, two packed instructions
 // (ptxas folds the swap of d into an operand swizzle)
@@ -166,8 +161,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * L::WIN_PITCH);
-    V3Meta* s_meta = reinterpret_cast<V3Meta*>(s_tw + 32 * L::TW_PITCH);
-    float* s_regions = reinterpret_cast<float*>(s_meta + WARPS);
+    float* s_regions = reinterpret_cast<float*>(s_tw + 32 * L::TW_PITCH);
 
     for (int i = threadIdx.x; i < 32 * L::WIN_PITCH; i += blockDim.x) {
         const int l = i / L::WIN_PITCH, j = i - l * L::WIN_PITCH;
@@ -429,20 +423,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_v3_kernel(PlanDev p, F
         }
         prev_valid = cur.valid;
         prev_row = cur.exists ? a.out + (((long long)cur.b * T_out + cur.t) * a.C_out + a.c_off) * 64 + 0 : nullptr;
-        if (lane == 0) {
-            V3Meta m;
-            m.out_row = a.out + (((long long)cur.b * T_out + cur.t) * a.C_out + a.c_off) * 64;
-            m.valid = cur.valid;
-            m.write = cur.exists;
-            s_meta[warp] = m;
-        }
         group_barrier(bar_id);  // the four frames of the group are in their planes
 
         // ---- mel phase: lane = (frame, channel); this warp owns filter chunk wi ----
         {
             const int f = lane >> 3, c = lane & 7;
-            const V3Meta m = s_meta[group * 4 + f];
-            if (c < NCH && m.write) {
+            if (c < NCH) {  // (slots of frames that do not exist hold finite dummy planes; their rows are never copied out)
                 const float* vp = gregion + f * L::REGION + c * L::PITCH;
                 float* orow = gregion + f * L::REGION + L::OUT_OFF + L::out_skew(f) + c * L::OUT_PITCH;
                 switch (wi) {
@@ -483,7 +469,7 @@ template <int R1, bool IV, int WARPS, bool REGSTASH>
 static int launch_v3_cfg(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
     using L = V3Layout<R1, REGSTASH>;
     auto kern = features_v3_kernel<R1, IV, WARPS, REGSTASH>;
-    const size_t smem = sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH) + sizeof(V3Meta) * WARPS +
+    const size_t smem = sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH) +
                         sizeof(float) * (size_t)WARPS * L::REGION;
     SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_gitems = (a.n_items + 3) / 4;
