@@ -10,6 +10,7 @@
 // Latency hiding with only 12 warps per SM (shared memory bound) is done by register prefetch: the raw
 // samples of channel pair b are requested before the post-processing of pair a, and the samples of the NEXT
 // frame's pair a before the mel gather of the current frame, when the FFT registers are dead.
+#include <algorithm>
 #include <cstdlib>
 
 #include "seld_common.h"
@@ -380,35 +381,42 @@ __global__ void __launch_bounds__(1024) feature_stats_kernel_v4(const float* __r
                                                                 const long long* __restrict__ lengths, long long n_samples,
                                                                 int hop, double* __restrict__ stats) {
     extern __shared__ double s_part[];  // [8][ncols4][8]
-    __shared__ unsigned char s_valid[kStatRows4];
+    __shared__ unsigned char s_valid[2][kStatRows4];
     const long long total_rows = (long long)B * T_out;
-    const long long r0 = (long long)blockIdx.x * kStatRows4;
-    const int n_rows = (int)min((long long)kStatRows4, total_rows - r0);
+    const long long n_slabs = (total_rows + kStatRows4 - 1) / kStatRows4;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if (tid < kStatRows4) {
-        bool ok = false;
-        if (tid < n_rows) {
-            const long long r = r0 + tid, b = r / T_out, t = r - b * T_out;
-            const long long lim = frames ? (long long)frames[b] : 1 + (lengths ? lengths[b] : n_samples) / hop;
-            ok = t < lim;
-        }
-        s_valid[tid] = ok;
-    }
-    __syncthreads();
     const int j = threadIdx.x;  // column quad
+    const int F4 = F / 4;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (j < ncols4) {
-        const float4* px = reinterpret_cast<const float4*>(x + r0 * F + col0) + j;
-        const int F4 = F / 4;
-#pragma unroll 8
-        for (int r = threadIdx.y; r < n_rows; r += 8) {
-            float4 v = __ldg(px + (long long)r * F4);
-            if (!s_valid[r]) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const double a0 = v.x, a1 = v.y, a2 = v.z, a3 = v.w;
-            acc[0] += a0; acc[1] += a1; acc[2] += a2; acc[3] += a3;
-            acc[4] = fma(a0, a0, acc[4]); acc[5] = fma(a1, a1, acc[5]);
-            acc[6] = fma(a2, a2, acc[6]); acc[7] = fma(a3, a3, acc[7]);
+    int buf = 0;
+    // persistent CTAs: the block reduction and the atomics happen once per CTA, not once per slab
+    for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, buf ^= 1) {
+        const long long r0 = slab * kStatRows4;
+        const int n_rows = (int)min((long long)kStatRows4, total_rows - r0);
+        if (tid < kStatRows4) {
+            bool ok = false;
+            if (tid < n_rows) {
+                const long long r = r0 + tid, b = r / T_out, t = r - b * T_out;
+                const long long lim = frames ? (long long)frames[b] : 1 + (lengths ? lengths[b] : n_samples) / hop;
+                ok = t < lim;
+            }
+            s_valid[buf][tid] = ok;
         }
+        __syncthreads();  // (double-buffered flags: one barrier per slab is enough)
+        if (j < ncols4) {
+            const float4* px = reinterpret_cast<const float4*>(x + r0 * F + col0) + j;
+#pragma unroll 8
+            for (int r = threadIdx.y; r < n_rows; r += 8) {
+                float4 v = __ldg(px + (long long)r * F4);
+                if (!s_valid[buf][r]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const double a0 = v.x, a1 = v.y, a2 = v.z, a3 = v.w;
+                acc[0] += a0; acc[1] += a1; acc[2] += a2; acc[3] += a3;
+                acc[4] = fma(a0, a0, acc[4]); acc[5] = fma(a1, a1, acc[5]);
+                acc[6] = fma(a2, a2, acc[6]); acc[7] = fma(a3, a3, acc[7]);
+            }
+        }
+    }
+    if (j < ncols4) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_part[(threadIdx.y * ncols4 + j) * 8 + i] = acc[i];
     }
@@ -452,7 +460,8 @@ int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t 
     if (F % 4 == 0 && col0 % 4 == 0 && ncols % 4 == 0 && ncols / 4 <= 128 &&
         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
         const int ncols4 = ncols / 4;
-        dim3 grid4((unsigned)((rows + kStatRows4 - 1) / kStatRows4)), block4((unsigned)((ncols4 + 31) / 32 * 32), 8);
+        const long long slabs = (rows + kStatRows4 - 1) / kStatRows4;
+        dim3 grid4((unsigned)std::min<long long>(slabs, 2ll * plan->num_sms)), block4((unsigned)((ncols4 + 31) / 32 * 32), 8);
         const size_t smem = sizeof(double) * 8 * ncols4 * 8;
         if (smem > 48 * 1024)
             SELD_CUDA_TRY(cudaFuncSetAttribute(feature_stats_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -102,7 +102,11 @@ __global__ void __launch_bounds__(kGccWarps * 32, 1) gcc_phat_kernel(PlanDev p, 
             {
                 float2 v[R1];
                 gcc_load_raw<R1>(v, x + (2 * pair) * a.chan_stride, x + (2 * pair + 1) * a.chan_stride, start, len, lane);
-                F::silent_channels(v, sil_a, sil_b);
+                // digitally silent channel?  cheap necessary test first (every lane's first sample is +-0), the OR over
+                // all raw samples only when it passes (rare, warp-uniform)
+                sil_a = !__any_sync(0xffffffffu, (__float_as_uint(v[0].x) << 1) != 0u);
+                sil_b = !__any_sync(0xffffffffu, (__float_as_uint(v[0].y) << 1) != 0u);
+                if (sil_a || sil_b) F::silent_channels(v, sil_a, sil_b);
 #pragma unroll
                 for (int j = 0; j < R1; ++j) {
                     v[j] = cscale(v[j], s_win[lane + 32 * j]);
