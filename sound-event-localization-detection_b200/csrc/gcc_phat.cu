@@ -42,10 +42,12 @@ __device__ __forceinline__ void gcc_load_raw(float2 (&v)[R1], const float* xa, c
     }
 }
 
-__device__ __forceinline__ float2 unit_phasor(float2 x) {
+// x / |x| scaled by keep (1, or 0 for a digitally silent channel); an exactly-zero bin stays (0, 0): the clamp keeps
+// rsqrt finite and 0 * finite = 0, so no select is needed
+__device__ __forceinline__ float2 unit_phasor(float2 x, float keep) {
     const float p = x.x * x.x + x.y * x.y;
-    const float r = rsqrtf(p);
-    return p > 0.f ? make_float2(x.x * r, x.y * r) : make_float2(0.f, 0.f);
+    const float r = rsqrtf(fmaxf(p, 1e-37f)) * keep;
+    return make_float2(x.x * r, x.y * r);
 }
 // conj(a) * b for unit (or zero) phasors; a zero operand means R == 0 -> exp(j*angle(0)) = 1
 __device__ __forceinline__ float2 phat(float2 a, float2 b) {
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(kGccWarps * 32, 1) gcc_phat_kernel(PlanDev p, 
             __syncwarp();
             F::pass2(u);
             float4* dst = pair ? S : Q;
+            const float keep_a = sil_a ? 0.f : 1.f, keep_b = sil_b ? 0.f : 1.f;
             static_for<16>([&](auto KH) {
                 constexpr int kh = decltype(KH)::value;
                 const float2 z = u[kh], m = u[31 - kh];
@@ -131,17 +134,13 @@ __global__ void __launch_bounds__(kGccWarps * 32, 1) gcc_phat_kernel(PlanDev p, 
                 pz.y = lane == 0 ? own.y : pz.y;
                 float2 xa, xb;
                 F::unpack(z, pz, xa, xb);
-                float2 ua = unit_phasor(xa), ub = unit_phasor(xb);
-                if (sil_a) ua = make_float2(0.f, 0.f);
-                if (sil_b) ub = make_float2(0.f, 0.f);
+                const float2 ua = unit_phasor(xa, keep_a), ub = unit_phasor(xb, keep_b);
                 dst[lane + R1 * kh] = make_float4(ua.x, ua.y, ub.x, ub.y);
             });
             if (lane == 0) {
                 float2 xa, xb;
                 F::unpack(u[16], u[16], xa, xb);
-                float2 ua = unit_phasor(xa), ub = unit_phasor(xb);
-                if (sil_a) ua = make_float2(0.f, 0.f);
-                if (sil_b) ub = make_float2(0.f, 0.f);
+                const float2 ua = unit_phasor(xa, keep_a), ub = unit_phasor(xb, keep_b);
                 dst[NB - 1] = make_float4(ua.x, ua.y, ub.x, ub.y);
             }
         }
