@@ -243,6 +243,18 @@ class SELDDataset(Dataset):
         return window['spectrogram'], window['labels']
 
     # ------------------------------------------------------------------------------------------
+    def scaler(self, group=None, device=None):
+        """Normalisation scaler of the whole (possibly rank-sharded) split: this dataset's per-feature partials
+        (``compute_stats=True``) merged, summed over all ranks with ONE all-reduce (NCCL on GPUs) and finalised."""
+        from .scaler import FeatureScaler
+        if self.stats is None:
+            raise ValueError("SELDDataset(compute_stats=True) is needed for scaler()")
+        sc = FeatureScaler(self.n_channels * self.n_mels, device if device is not None else self.device)
+        sc.merge(self.stats, self.total_frames)
+        sc.sync(group)
+        sc.finalize()
+        return sc
+
     def _events_sorted(self):
         """Event table sorted by first row (stable), built once; painting order inside a window does not matter
         (the paint kernel's two passes are order-independent)."""
@@ -290,6 +302,22 @@ def shard_clips(n_clips: int, rank: int, world_size: int):
     base, extra = divmod(int(n_clips), int(world_size))
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_files(audio_files, metadata_files, rank=None, world_size=None):
+    """This rank's contiguous block of the (audio, metadata) file lists — ``load_files()`` output sharded for one
+    process per GPU.  ``rank`` / ``world_size`` default to ``torch.distributed`` (if initialised) or RANK / WORLD_SIZE."""
+    import os
+
+    import torch.distributed as dist
+    if rank is None or world_size is None:
+        if dist.is_available() and dist.is_initialized():
+            rank, world_size = dist.get_rank(), dist.get_world_size()
+        else:
+            rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    assert len(audio_files) == len(metadata_files), "Number of audio files must match number of metadata files"
+    lo, hi = shard_clips(len(audio_files), rank, world_size)
+    return list(audio_files[lo:hi]), list(metadata_files[lo:hi])
 
 
 def _lib_mode(mode: str) -> int:

@@ -51,6 +51,17 @@ def test_shard_clips_contiguous_balanced():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_files_uses_rank_env(monkeypatch):
+    sys.path.insert(0, ROOT)
+    from seld_b200.dataset import shard_files
+    a, m = [f"a{i}.wav" for i in range(7)], [f"a{i}.csv" for i in range(7)]
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "3")
+    assert shard_files(a, m) == (a[3:5], m[3:5])
+    got = [shard_files(a, m, r, 3) for r in range(3)]
+    assert sum((g[0] for g in got), []) == a and sum((g[1] for g in got), []) == m
+
+
 @pytest.mark.timeout(120)
 def test_scaler_allreduce_two_ranks_gloo():
     g = torch.Generator().manual_seed(0)
