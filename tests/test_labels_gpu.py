@@ -173,6 +173,8 @@ def test_scaler_stats_apply(sb):
     m_ref, s_ref = of.scaler_mean_std(c, s, ss)
     assert np.allclose(mean.cpu().numpy(), m_ref, rtol=1e-6, atol=1e-6)
     assert np.allclose(std.cpu().numpy(), s_ref, rtol=1e-5, atol=1e-6)
+    sc2 = ds.scaler()  # the one-call form (merge + all-reduce + finalize)
+    assert torch.equal(sc2.mean, mean) and torch.equal(sc2.std, std)
     x = ds._features_tcf.clone()
     sc.apply(x)
     want = (f - m_ref) / s_ref
