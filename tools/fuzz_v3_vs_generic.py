@@ -3,9 +3,11 @@ ragged lengths, strides, frame capacities, silent channels, both n_fft.  usage (
 import os, sys, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 import seld_b200 as sb
-rng = np.random.default_rng(123)
+seed = int(sys.argv[1]) if len(sys.argv) > 1 else 123
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+rng = np.random.default_rng(seed)
 worst = 0
-for it in range(60):
+for it in range(iters):
     n_fft = int(rng.choice([1024, 960]))
     B = int(rng.integers(1, 6))
     nmax = int(rng.integers(600, 60000))
