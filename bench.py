@@ -315,6 +315,12 @@ def main():
     if args.workload != "foa":
         return run_aux(args)
 
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 from C (NCCL prints its version there)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -460,7 +466,10 @@ def main():
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
