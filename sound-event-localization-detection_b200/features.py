@@ -78,9 +78,27 @@ class FeaturePlan:
 
     def run(self, audio: torch.Tensor, mode="logmel", lengths: torch.Tensor | None = None, out: torch.Tensor | None = None,
             c_off: int = 0, stats: torch.Tensor | None = None, stat_frames: torch.Tensor | None = None,
-            spec: torch.Tensor | None = None, T_out: int | None = None) -> torch.Tensor:
-        """audio (B, C, N) float32 CUDA (any strides with unit sample stride) -> (B, T_out, C_out, n_mels)."""
+            spec: torch.Tensor | None = None, T_out: int | None = None, isolate_channels: bool = False) -> torch.Tensor:
+        """audio (B, C, N) float32 CUDA (any strides with unit sample stride) -> (B, T_out, C_out, n_mels).
+
+        ``isolate_channels`` (log-mel mode only): transform every channel on its own, like the reference does
+        (dataset.py:46-50), instead of two channels per complex FFT.  About 2.5x slower; removes the rounding-noise
+        coupling between paired channels that shows when their levels differ by more than ~45 dB."""
         mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        if isolate_channels:
+            if mode != SELD_MODE_LOGMEL or spec is not None:
+                raise ValueError("isolate_channels is available for mode='logmel' without a spectrum dump")
+            Cn = audio.shape[1]
+            if T_out is None:
+                T_out = self.num_frames(audio.shape[2])
+            if out is None:
+                out = torch.empty((audio.shape[0], T_out, c_off + Cn, self.n_mels), dtype=torch.float32, device=self.device)
+            for c in range(Cn):  # a one-channel group pairs the channel with an exact zero: nothing can leak into it
+                self.run(audio[:, c:c + 1], mode=mode, lengths=lengths, out=out, c_off=c_off + c, T_out=T_out)
+            if stats is not None:
+                self.accumulate_stats(out, stats, n_samples=audio.shape[2], lengths=lengths, stat_frames=stat_frames,
+                                      c_off=c_off, n_channels=Cn)
+            return out
         if audio.dim() != 3:
             raise ValueError("audio must be (B, C, N)")
         if audio.dtype != torch.float32 or not audio.is_cuda:
@@ -163,7 +181,7 @@ def _default(name):
 
 
 def audio_to_mel_spectrogram(waveform: torch.Tensor, sample_rate: int, n_fft=None, hop_length=None, n_mels=None,
-                             device=None) -> torch.Tensor:
+                             device=None, isolate_channels: bool = False) -> torch.Tensor:
     """Drop-in for reference dataset.py:27-58: (C, N) waveform -> (C, n_mels, 1 + N//hop) float32 dB.
 
     ``None`` arguments fall back to the Config values like the reference (dataset.py:30-35).  A CPU waveform
@@ -182,7 +200,7 @@ def audio_to_mel_spectrogram(waveform: torch.Tensor, sample_rate: int, n_fft=Non
     dev = torch.device(device) if device is not None else (waveform.device if waveform.is_cuda else torch.device("cuda"))
     x = waveform.to(device=dev, dtype=torch.float32, non_blocking=True)
     plan = get_plan(n_fft, hop_length, n_mels, sample_rate, x.device)
-    out = plan.run(x.unsqueeze(0), mode="logmel")[0]  # (T, C, M)
+    out = plan.run(x.unsqueeze(0), mode="logmel", isolate_channels=isolate_channels)[0]  # (T, C, M)
     res = out.permute(1, 2, 0)
     return res.contiguous().cpu() if was_cpu else res
 

@@ -188,3 +188,15 @@ def test_packed_fft_crosstalk_is_bounded(sb, n_fft):
         e = np.abs(y - ref)
         assert max(e[:, 0].max(), e[:, 3].max()) <= bound, level_db
         assert max(e[:, 1].max(), e[:, 2].max()) <= TOL_DB
+
+
+def test_isolated_channels_have_no_crosstalk(sb):
+    """isolate_channels=True transforms each channel alone (paired with an exact zero), like the reference: the quiet
+    channel keeps the 1e-3 dB bar even 100 dB below its neighbours."""
+    rng = np.random.default_rng(5)
+    x = (0.2 * rng.standard_normal((4, 24000))).astype(np.float32)
+    x[0] *= 1e-5
+    x[3] *= 1e-5
+    y = _feat(sb, x, 1024, "logmel", isolate_channels=True)[0]
+    ref = of.logmel(x, 24000, 1024, 480, 64).transpose(2, 0, 1)
+    assert np.abs(y - ref).max() <= TOL_DB
