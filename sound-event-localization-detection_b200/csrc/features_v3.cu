@@ -8,14 +8,18 @@
 // pipe; v3 is organised around shared-memory wavefronts per frame:
 //   * warps work in groups of four.  Phase A: every warp transforms one frame (all four channels, two
 //     packed complex FFTs) exactly like v2, but leaves its per-bin features as seven PLANES
-//     V[c][k] (P0 P1 P2 P3 I1/E I2/E I3/E) in its own shared-memory region.  The spectra of the first
-//     channel pair are parked in planes 0..3 (same lane, same bin: in place), the transpose tile lives
-//     behind them where planes 4..6 go later.
+//     V[c][k] (P0 P1 P2 P3 I1/E I2/E I3/E) in its own shared-memory region.  What the second channel pair
+//     needs from the first (X0, |X1|^2, Re(conj(X0) X1)) is parked in planes 0..3 (same lane, same bin: in
+//     place), the transpose tile lives behind them where planes 4..6 and the staged output row go later.
 //   * Phase B (after a 128-thread named barrier): the four warps project the group's four frames onto the
 //     mel filters.  Lane = (frame, channel), so all lanes walk the SAME bins: the filterbank is baked into
 //     the instruction stream (mel_baked.h: weights are FFMA immediates, filter boundaries are straight-line
 //     code), every plane word is read exactly once (no gather tables, no padding, no bank conflicts) and
-//     each warp owns a quarter of the filters.  Results go to global memory as 16-byte stores.
+//     each warp owns a quarter of the filters (balanced by instruction count).  The raw mel energies are
+//     staged behind the planes; after the group's next barrier the owning warp applies 10 log10 and writes
+//     the frame's 1792-byte row with coalesced 128-byte stores.
+//   * arithmetic is packed where the data come in pairs (add/sub/mul/fma.rn.f32x2 -> FADD2/FMUL2/FFMA2 on
+//     sm_100a): butterflies, window, channel split, power pairs.
 #include <cstdlib>
 
 #include "mel_baked.h"
@@ -23,7 +27,6 @@
 #include "warp_fft.cuh"
 
 namespace seld {
-
 
 template <int R1, bool REGSTASH>
 struct V3Layout {
