@@ -14,6 +14,10 @@
  *  - Return value: 0 = OK, negative = seld_status.  Nothing aborts or throws across the boundary;
  *    seld_last_error() returns a thread-local message for the last failing call on this thread.
  *  - There is no CPU fallback: without a CUDA device every compute call returns SELD_ERR_CUDA.
+ *  - Every entry point runs on the device of its plan (or of its output pointer) and RESTORES the caller's current
+ *    device before returning: a process that drives several GPUs can call from any thread with any current device.
+ *  - The hot calls do no host work besides argument checks and the launch: environment switches (SELD_FEAT_IMPL,
+ *    SELD_V3_CFG) are read and kernel attributes are set once, in seld_plan_create.
  */
 #ifndef SELD_CUDA_H
 #define SELD_CUDA_H
@@ -60,7 +64,7 @@ SELD_API int seld_out_channels(int mode, int n_channels);
  * (torchaudio.transforms.MelSpectrogram: Hann window + HTK filterbank).
  *   h_window : n_fft floats, the analysis window (torch.hann_window(n_fft), float32)
  *   h_fb     : (n_fft/2+1, n_mels) row-major float32 filterbank (melscale_fbanks(...))
- * n_fft in {960, 1024}; n_mels <= 64. */
+ * n_fft in {960, 1024}; n_mels <= 64.  GCC-PHAT mode: n_mels == 64 (= lags). */
 SELD_API int seld_plan_create(seld_plan** plan, int device, int n_fft, int hop, int n_mels, const float* h_window,
                      const float* h_fb);
 SELD_API int seld_plan_destroy(seld_plan* plan);
@@ -68,7 +72,8 @@ SELD_API int seld_plan_destroy(seld_plan* plan);
 /* Fused framing + window + real FFT + power + mel + 10*log10 (+ IV | + GCC-PHAT).
  * Replaces reference dataset.py:27-58 audio_to_mel_spectrogram for a whole batch of clips.
  *   d_audio      : float32, clip b channel c sample n at d_audio[b*clip_stride + c*chan_stride + n]
- *   d_lengths    : int64[B] valid samples per clip, or NULL (all = n_samples); each must be > n_fft/2
+ *   d_lengths    : int64[B] valid samples per clip, or NULL (all = n_samples); each must be > n_fft/2 (a shorter
+ *                  clip is flagged on the device, see seld_plan_status, and its rows are written as 0)
  *   d_out        : float32 (B, T_out, C_out, n_mels), frame-major ("TCM") — the layout the reference's
  *                  models consume after dataset.py:303; rows t >= 1 + len_b/hop are written as 0
  *   T_out        : frame capacity per clip (>= seld_num_frames(max length))
@@ -76,13 +81,54 @@ SELD_API int seld_plan_destroy(seld_plan* plan);
  *   c_off        : first output channel to write
  *   d_stats      : optional float64[2 * C_out * n_mels]: the call ADDS per-feature sum and sum of squares
  *                  of the values it writes for frames t < d_stat_frames[b] (or all valid frames when
- *                  d_stat_frames is NULL) — the normalisation-scaler partials
+ *                  d_stat_frames is NULL) — the normalisation-scaler partials.  On the fast
+ *                  path the sums are formed inside the feature kernel (fp32 partials of <= 64 rows, flushed into
+ *                  the float64 sums: relative error ~1e-7); otherwise by a second kernel over d_out.
  *   d_spec       : optional float32 complex (B, C, T_out, n_fft/2+1) dump of the STFT (parity tests)
  */
 SELD_API int seld_features(seld_plan* plan, int mode, const float* d_audio, int64_t clip_stride, int64_t chan_stride,
                   int64_t n_samples, const int64_t* d_lengths, int B, int C, float* d_out, int64_t T_out,
                   int C_out, int c_off, double* d_stats, const int32_t* d_stat_frames, float* d_spec,
                   void* stream);
+
+/* seld_features with input / output options (fast path only: 4 channels, the reference's 64-mel HTK bank, no spectrum
+ * dump, 16-byte aligned output; SELD_ERR_UNSUPPORTED otherwise).
+ *   in_dtype   : SELD_DTYPE_F32, or SELD_DTYPE_I16 — d_audio holds 16-bit PCM and the kernel converts x / 32768 while
+ *                loading (what torchaudio.load returns for a 16-bit WAV, the decode half of reference dataset.py:18-25
+ *                load_audio): half the PCIe / HBM bytes per sample, no separate conversion pass
+ *   out_layout : SELD_LAYOUT_TCF (B, T, C, F) as seld_features, or SELD_LAYOUT_CTF (B, C, T, F) — the layout every
+ *                reference model permutes to first (model_crnn.py:106, model_conformer.py:191, resnet50_model.py:179)
+ *   out_dtype  : SELD_DTYPE_F32 or SELD_DTYPE_BF16
+ *   d_mean, d_inv_std : float32[C_out * n_mels] or both NULL; when given the kernel writes (x - mean) * inv_std of the
+ *                valid rows (rows past a clip's end stay 0) — the scaler apply step fused into the row copy-out.
+ * d_stats cannot be combined with normalisation / layout / dtype options (the partials are those of the raw features).
+ * opts == NULL is seld_features.  d_out is float32 or bfloat16 according to out_dtype. */
+#define SELD_DTYPE_F32 0
+#define SELD_DTYPE_I16 1
+#define SELD_DTYPE_BF16 2
+#define SELD_LAYOUT_TCF 0
+#define SELD_LAYOUT_CTF 1
+typedef struct seld_feat_opts {
+    int in_dtype;
+    int out_layout;
+    int out_dtype;
+    const float* d_mean;
+    const float* d_inv_std;
+} seld_feat_opts;
+SELD_API int seld_features_ex(seld_plan* plan, int mode, const void* d_audio, int64_t clip_stride, int64_t chan_stride,
+                     int64_t n_samples, const int64_t* d_lengths, int B, int C, void* d_out, int64_t T_out,
+                     int C_out, int c_off, double* d_stats, const int32_t* d_stat_frames, float* d_spec,
+                     const seld_feat_opts* opts, void* stream);
+
+/* 1 if the plan's filterbank is the reference's (64 HTK mels of a 24 kHz / n_fft 960|1024 STFT, bit for bit) so that
+ * 4-channel calls run on the fast kernel — the precondition of seld_features_ex options; 0 otherwise. */
+SELD_API int seld_plan_has_fast_path(const seld_plan* plan);
+
+/* Device-side status of the calls issued so far on `stream` with this plan: synchronises the stream, copies the
+ * status word back, clears it.  *h_status bit 0: some clip of a ragged batch (d_lengths) had <= n_fft/2 samples —
+ * torch.stft(center=True, pad_mode="reflect") raises for those (reference dataset.py:49); the kernels read nothing
+ * from such a clip and write its rows as 0.  Returns SELD_ERR_BAD_ARG when a bit is set, SELD_OK otherwise. */
+SELD_API int seld_plan_status(seld_plan* plan, void* stream, int* h_status);
 
 /* Scaler partials of an already computed feature tensor (the accumulation seld_features performs when given
  * d_stats, as a call of its own): for the channels [c_off, c_off + n_channels) of d_feat (B, T_out, C_out, n_mels)

@@ -11,6 +11,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseld_cuda.so")
 
 SELD_MODE_LOGMEL, SELD_MODE_LOGMEL_IV, SELD_MODE_LOGMEL_GCC = 0, 1, 2
+SELD_DTYPE_F32, SELD_DTYPE_I16, SELD_DTYPE_BF16 = 0, 1, 2
+SELD_LAYOUT_TCF, SELD_LAYOUT_CTF = 0, 1
+
+
+class FeatOpts(C.Structure):
+    """``seld_feat_opts`` (include/seld_cuda.h)."""
+    _fields_ = [("in_dtype", C.c_int), ("out_layout", C.c_int), ("out_dtype", C.c_int), ("d_mean", C.c_void_p),
+                ("d_inv_std", C.c_void_p)]
 
 
 class SeldError(RuntimeError):
@@ -29,6 +37,11 @@ _SIGS = {
     "seld_features": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "seld_features_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(FeatOpts), C.c_void_p]),
+    "seld_plan_status": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "seld_plan_has_fast_path": (C.c_int, [C.c_void_p]),
     "seld_feature_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "seld_scaler_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

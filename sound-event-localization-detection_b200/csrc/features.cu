@@ -12,7 +12,9 @@
 // frame's pair a before the mel gather of the current frame, when the FFT registers are dead.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
+#include "features_fast.cuh"
 #include "seld_common.h"
 #include "warp_fft.cuh"
 
@@ -33,6 +35,9 @@ __device__ __forceinline__ void load_raw(float2 (&v)[R1], const float* xa, const
 #pragma unroll
             for (int j = 0; j < R1; ++j) v[j] = make_float2(__ldg(pa + 32 * j), 0.f);
         }
+    } else if (len <= F::HALF) {  // too short for reflect padding: nothing is read, the rows are written as 0
+#pragma unroll
+        for (int j = 0; j < R1; ++j) v[j] = make_float2(0.f, 0.f);
     } else {
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
@@ -42,19 +47,39 @@ __device__ __forceinline__ void load_raw(float2 (&v)[R1], const float* xa, const
     }
 }
 
-// window -> pass 1 -> transpose -> pass 2; result in u (lane = k_lo, register = k_hi)
+// window -> pass 1 -> transpose -> pass 2; result in u (lane = k_lo, register = k_hi).
+// Block floating point as in the fast kernel (features_fast.cuh): max |windowed x| of both channels over the warp; 0 <=>
+// digitally silent (bits_* = 0); when the binary exponents differ by >= 4 the quieter channel is multiplied by the exact power of
+// two that brings it to its partner's level, and inv_a / inv_b (applied to the split spectra by the caller) undo it.
 template <int R1>
 __device__ __forceinline__ void fft_from_raw(float2 (&u)[32], float2 (&v)[R1], const float* s_win, const float2* s_tw,
-                                             float2* T, int lane, unsigned& bits_a, unsigned& bits_b) {
+                                             float2* T, int lane, unsigned& bits_a, unsigned& bits_b, float& inv_a,
+                                             float& inv_b) {
     using F = WarpFft<R1>;
-    bits_a = bits_b = 0u;  // OR of the raw sample bits: all-zero channel detection (voted on after the FFT)
+    float ma = 0.f, mb = 0.f;
 #pragma unroll
-    for (int j = 0; j < R1; ++j) {
+    for (int j = 0; j < R1; ++j) {  // window first: the level that matters is that of what enters the FFT
         const float w = s_win[lane + 32 * j];
-        bits_a |= __float_as_uint(v[j].x);
-        bits_b |= __float_as_uint(v[j].y);
         v[j].x *= w;
         v[j].y *= w;
+        ma = fmaxf(ma, fabsf(v[j].x));
+        mb = fmaxf(mb, fabsf(v[j].y));
+    }
+    bits_a = __reduce_max_sync(0xffffffffu, __float_as_uint(ma));
+    bits_b = __reduce_max_sync(0xffffffffu, __float_as_uint(mb));
+    int sh = (int)(bits_a >> 23) - (int)(bits_b >> 23);
+    sh = (bits_a == 0u || bits_b == 0u) ? 0 : sh;
+    sh = (sh > -4 && sh < 4) ? 0 : max(-60, min(60, sh));
+    const int sa = sh < 0 ? -sh : 0, sb = sh > 0 ? sh : 0;
+    const float fa = __uint_as_float((unsigned)(127 + sa) << 23), fb = __uint_as_float((unsigned)(127 + sb) << 23);
+    inv_a = __uint_as_float((unsigned)(127 - sa) << 23);
+    inv_b = __uint_as_float((unsigned)(127 - sb) << 23);
+    if (sh != 0) {
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+            v[j].x *= fa;
+            v[j].y *= fb;
+        }
     }
     F::pass1(v, s_tw + lane);
     __syncwarp();  // every lane is done reading whatever lived in T / R before
@@ -77,6 +102,7 @@ __device__ __forceinline__ void split_pair(const float2 (&u)[32], int lane, int 
     p.y = lane == 0 ? own.y : p.y;
     WarpFft<R1>::unpack(z, p, xa, xb);
 }
+__device__ __forceinline__ float2 fscale(float2 x, float f) { return make_float2(x.x * f, x.y * f); }
 
 struct ItemCtx {
     const float* x;     // channel c0 of the clip
@@ -87,8 +113,9 @@ struct ItemCtx {
     bool valid;         // t < T_b (padding rows of a ragged batch are written as 0)
 };
 
-template <int R1, bool IV, bool SPEC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, FeatArgs a) {
+template <int R1, bool IV, bool SPEC>
+__global__ void __launch_bounds__(kFeatWarps * 32, 1) features_kernel(PlanDev p, FeatArgs a) {
+    const int WARPS = blockDim.x >> 5;  // chosen at plan creation from the shared-memory budget (<= kFeatWarps)
     using F = WarpFft<R1>;
     constexpr int N = F::N, NB = F::NB;
     constexpr int NCH = IV ? 7 : 4;
@@ -136,9 +163,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
         c.len = len_cache;
         const int c0 = 4 * (int)g;
         c.nch = min(4, a.C - c0);
-        c.valid = (long long)t_ < 1 + c.len / p.hop;
+        const bool too_short = c.len <= F::HALF;  // reflect padding undefined (torch raises): rows written as 0 + status bit
+        if (a.lengths && too_short && t_ == 0 && lane == 0) atomicOr(a.status, 1);
+        c.valid = (long long)t_ < 1 + c.len / p.hop && !too_short;
         c.start = c.valid ? (long long)t_ * p.hop - F::HALF : 0;  // padding rows read frame 0 and are zeroed at the store
-        c.x = a.audio + b * a.clip_stride + (long long)c0 * a.chan_stride;
+        c.x = reinterpret_cast<const float*>(a.audio) + b * a.clip_stride + (long long)c0 * a.chan_stride;
         c.out_row = a.out + ((b * a.T_out + t_) * a.C_out + a.c_off + c0) * n_mels;
         c.spec = SPEC ? a.spec + ((b * a.C + c0) * a.T_out + t_) * NB : nullptr;
         return c;
@@ -153,7 +182,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
         const long long spec_cs = a.T_out * NB;  // channel stride of the spectrum dump
         // ================= channel pair (c0, c0+1) =================
         unsigned bits_a, bits_b;
-        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, bits_a, bits_b);
+        float inv_a, inv_b;
+        fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, bits_a, bits_b, inv_a, inv_b);
         const bool have_b = cur.nch > 2;
         if (have_b)  // request pair b now; it lands while pair a is post-processed
             load_raw<R1>(v, cur.x + 2 * a.chan_stride, cur.nch > 3 ? cur.x + 3 * a.chan_stride : nullptr, cur.start,
@@ -162,6 +192,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
             constexpr int kh = decltype(KH)::value;
             float2 x0, x1;
             split_pair<R1, kh>(u, lane, src, x0, x1);
+            x0 = fscale(x0, inv_a);
+            x1 = fscale(x1, inv_b);
             const int k = lane + R1 * kh;
             if (active) {
                 Q[k] = make_float4(x0.x, x0.y, x1.x, x1.y);
@@ -174,6 +206,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
         if (lane == 0) {  // Nyquist bin: its own mirror
             float2 x0, x1;
             F::unpack(u[16], u[16], x0, x1);
+            x0 = fscale(x0, inv_a);
+            x1 = fscale(x1, inv_b);
             Q[NB - 1] = make_float4(x0.x, x0.y, x1.x, x1.y);
             if (SPEC) {
                 cur.spec[NB - 1] = x0;
@@ -182,8 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
         }
         // A silent channel must come out as an exactly-zero spectrum like the reference's separate FFT; the
         // split leaves the rounding asymmetry of the other channel (~1e-7 relative) in it.
-        const bool sil_a = !__any_sync(0xffffffffu, (bits_a << 1) != 0u);
-        const bool sil_b = !__any_sync(0xffffffffu, (bits_b << 1) != 0u);
+        const bool sil_a = bits_a == 0u, sil_b = bits_b == 0u;
         if (sil_a || sil_b) {  // rare (warp-uniform)
             const float ka = sil_a ? 0.f : 1.f, kb = sil_b ? 0.f : 1.f;
             __syncwarp();
@@ -199,8 +232,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
         }
         // ================= channel pair (c0+2, c0+3) =================
         unsigned bits_c = 0u, bits_d = 0u;
+        float inv_c = 1.f, inv_d = 1.f;
         if (have_b) {
-            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, bits_c, bits_d);
+            fft_from_raw<R1>(u, v, s_win, s_tw, T, lane, bits_c, bits_d, inv_c, inv_d);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) u[i] = make_float2(0.f, 0.f);
@@ -210,6 +244,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
             constexpr int kh = decltype(KH)::value;
             float2 x2, x3;
             split_pair<R1, kh>(u, lane, src, x2, x3);
+            x2 = fscale(x2, inv_c);
+            x3 = fscale(x3, inv_d);
             const int k = lane + R1 * kh;
             if (active) {
                 const float4 s = Q[k];
@@ -226,6 +262,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
         if (lane == 0) {
             float2 x2, x3;
             F::unpack(u[16], u[16], x2, x3);
+            x2 = fscale(x2, inv_c);
+            x3 = fscale(x3, inv_d);
             const float4 s = Q[NB - 1];
             float4 q, r;
             bin_features<IV>(make_float2(s.x, s.y), make_float2(s.z, s.w), x2, x3, q, r);
@@ -236,8 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(PlanDev p, Feat
                 if (cur.nch > 3) cur.spec[3 * spec_cs + NB - 1] = x3;
             }
         }
-        const bool sil_c = !__any_sync(0xffffffffu, (bits_c << 1) != 0u);
-        const bool sil_d = !__any_sync(0xffffffffu, (bits_d << 1) != 0u);
+        const bool sil_c = bits_c == 0u, sil_d = bits_d == 0u;
         if (have_b && (sil_c || sil_d)) {  // rare (warp-uniform): redo the rows with the silent channel at exactly 0
             __syncwarp();
             for (int k = lane; k < NB; k += 32) {
@@ -432,23 +469,23 @@ __global__ void __launch_bounds__(1024) feature_stats_kernel_v4(const float* __r
     }
 }
 
-template <int R1, bool IV, bool SPEC, int WARPS>
-static int launch_one(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    auto kern = features_kernel<R1, IV, SPEC, WARPS>;
-    const size_t smem = plan->table_bytes + (size_t)WARPS * plan->warp_smem;
-    SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = (a.n_items + WARPS - 1) / WARPS;
+template <int R1, bool IV, bool SPEC>
+static int launch_w(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
+    const int warps = plan->generic_warps;  // from the shared-memory budget of this plan's tables (seld_plan_create)
+    const size_t smem = plan->table_bytes + (size_t)warps * plan->warp_smem;
+    long long ctas = (a.n_items + warps - 1) / warps;
     if (ctas > plan->num_sms) ctas = plan->num_sms;
     if (ctas < 1) return SELD_OK;
-    kern<<<(unsigned)ctas, WARPS * 32, smem, stream>>>(plan->dev, a);
+    features_kernel<R1, IV, SPEC><<<(unsigned)ctas, warps * 32, smem, stream>>>(plan->dev, a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }
 
-// 12 warps per CTA fill the 227 KB of shared memory (168 registers per thread)
 template <int R1, bool IV, bool SPEC>
-static int launch_w(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    return launch_one<R1, IV, SPEC, kFeatWarps>(plan, a, stream);
+static int configure_w(const seld_plan* plan) {
+    (void)plan;  // the attribute is a per-function maximum: opt in to the whole 227 KB once, every plan fits below it
+    SELD_CUDA_TRY(cudaFuncSetAttribute(features_kernel<R1, IV, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    return SELD_OK;
 }
 
 int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
@@ -463,8 +500,6 @@ int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t 
         const long long slabs = (rows + kStatRows4 - 1) / kStatRows4;
         dim3 grid4((unsigned)std::min<long long>(slabs, 2ll * plan->num_sms)), block4((unsigned)((ncols4 + 31) / 32 * 32), 8);
         const size_t smem = sizeof(double) * 8 * ncols4 * 8;
-        if (smem > 48 * 1024)
-            SELD_CUDA_TRY(cudaFuncSetAttribute(feature_stats_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         feature_stats_kernel_v4<<<grid4, block4, smem, stream>>>(a.out, a.T_out, F, col0, ncols4, a.B, a.stat_frames,
                                                                   a.lengths, a.n_samples, plan->dev.hop, a.stats);
         SELD_CUDA_TRY(cudaGetLastError());
@@ -477,23 +512,101 @@ int launch_feature_stats(const seld_plan* plan, const FeatArgs& a, cudaStream_t 
     return SELD_OK;
 }
 
-int launch_features_v3(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream);
+// Does the caller's filterbank equal the baked one bit for bit?  (host, at plan creation)
+template <int NFFT>
+static bool fb_matches(const float* fb, int n_mels) {
+    using MB = MelBaked<NFFT>;
+    if (n_mels != MB::N_MELS) return false;
+    for (int k = 0; k < MB::NB; ++k)
+        for (int m = 0; m < n_mels; ++m) {
+            float want = 0.f;
+            if (m == MB::m0[k]) want = MB::w0[k];
+            if (m == MB::m1[k]) want = MB::w1[k];
+            if (fb[(size_t)k * n_mels + m] != want) return false;
+        }
+    return true;
+}
+bool fast_filterbank_matches(int n_fft, const float* fb, int n_mels) {
+    return n_fft == 1024 ? fb_matches<1024>(fb, n_mels) : n_fft == 960 ? fb_matches<960>(fb, n_mels) : false;
+}
 
-// SELD_FEAT_IMPL=v2 forces the generic kernel (A/B measurements; read per call so one process can time both)
-static bool v3_enabled() {
-    const char* e = getenv("SELD_FEAT_IMPL");
-    return !(e && e[0] == 'v' && e[1] == '2');
+// One-time kernel configuration for a plan's device (cudaFuncSetAttribute is per device): called by seld_plan_create
+// so that the hot calls do no host work besides the launch.
+int configure_feature_kernels(const seld_plan* plan) {
+    int rc = SELD_OK;
+    auto acc = [&](int r) { if (rc == SELD_OK) rc = r; };
+    {
+        cudaError_t e = cudaFuncSetAttribute(feature_stats_kernel_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 8 * (int)sizeof(double));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(feature_stats_kernel_v4)");
+    }
+    if (plan->dev.r1 == 32) {
+        acc(configure_w<32, true, true>(plan)); acc(configure_w<32, true, false>(plan));
+        acc(configure_w<32, false, true>(plan)); acc(configure_w<32, false, false>(plan));
+        if (plan->v3_ok) { acc(fast_configure_r32_f32()); acc(fast_configure_r32_i16()); }
+    } else {
+        acc(configure_w<30, true, true>(plan)); acc(configure_w<30, true, false>(plan));
+        acc(configure_w<30, false, true>(plan)); acc(configure_w<30, false, false>(plan));
+        if (plan->v3_ok) { acc(fast_configure_r30_f32()); acc(fast_configure_r30_i16()); }
+    }
+    return rc;
+}
+
+// Redo list of the stream a call runs on.  Calls on one stream are ordered, so a slot is never shared by two calls in
+// flight; the first kRedoSlots streams that use a plan get a slot each, later ones get none (block floating on every
+// frame then, ~8 % slower).  Host-only bookkeeping: a mutex and a 16-entry table, no CUDA call.
+static_assert(kRedoCap == (1 << 16), "abi.cu sizes the redo lists with this capacity");
+unsigned* plan_redo_slot(seld_plan* plan, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(plan->slot_mutex));
+    for (int i = 0; i < plan->n_slots; ++i)
+        if (plan->slot_stream[i] == (void*)stream) return plan->d_redo + (size_t)i * (4 + kRedoCap);
+    if (plan->n_slots >= kRedoSlots) return nullptr;
+    plan->slot_stream[plan->n_slots] = (void*)stream;
+    return plan->d_redo + (size_t)(plan->n_slots++) * (4 + kRedoCap);
+}
+
+// fast path: the reference's own configurations (4 channels, baked 64-mel HTK bank), 16-byte aligned rows
+bool fast_path_ok(const seld_plan* plan, const FeatArgs& a) {
+    return plan->v3_ok && !plan->force_generic && a.C == 4 && a.spec == nullptr &&
+           (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
 }
 
 int launch_features(const seld_plan* plan, bool iv, const FeatArgs& a, cudaStream_t stream) {
     const bool sp = a.spec != nullptr;
+    const bool ext = a.mean || a.inv_std || a.out_ctf || a.out_bf16;
     int rc;
-    // fast path: the reference's own configurations (4 channels, baked 64-mel HTK bank), 16-byte aligned rows
-    if (plan->v3_ok && a.C == 4 && !sp && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && v3_enabled()) {
-        rc = launch_features_v3(plan, iv, a, stream);
+    if (fast_path_ok(plan, a)) {
+        if (ext && a.stats) {  // the partials are those of the raw float32 features
+            set_error("seld_features_ex: d_stats cannot be combined with normalisation / layout / bf16 options");
+            return SELD_ERR_UNSUPPORTED;
+        }
+        const int epi = ext ? 2 : 0;
+        const int warps = a.in_i16 ? 12 : plan->fast_warps;
+        auto run = [&](bool bf, const FeatArgs& fa) {
+            if (plan->dev.r1 == 32)
+                return fa.in_i16 ? fast_launch_r32_i16(plan, iv, epi, 12, bf, fa, stream)
+                                 : fast_launch_r32_f32(plan, iv, epi, warps, bf, fa, stream);
+            return fa.in_i16 ? fast_launch_r30_i16(plan, iv, epi, 12, bf, fa, stream)
+                             : fast_launch_r30_f32(plan, iv, epi, warps, bf, fa, stream);
+        };
+        FeatArgs fa = a;
+        fa.redo = plan_redo_slot(const_cast<seld_plan*>(plan), stream);
+        if (plan->force_bf || !fa.redo) {  // A/B switch, or more streams than slots: block floating on every frame
+            fa.redo_mode = 0;
+            rc = run(true, fa);
+        } else {
+            fa.redo_mode = 0;
+            rc = run(false, fa);           // lean kernel: all frames, flags the ones whose channel pairs differ too much
+            if (rc != SELD_OK) return rc;
+            fa.redo_mode = 1;
+            rc = run(true, fa);            // block-floating kernel: the same (persistent) grid over the flagged frames
+        }
         if (rc != SELD_OK) return rc;
-        if (a.stats) return launch_feature_stats(plan, a, stream);
-        return SELD_OK;
+        return a.stats ? launch_feature_stats(plan, a, stream) : SELD_OK;
+    }
+    if (a.in_i16 || ext) {
+        set_error("seld_features_ex: int16 input and the output options need the fast path (4 channels, 64 HTK mels, "
+                  "no spectrum dump, 16-byte aligned output)");
+        return SELD_ERR_UNSUPPORTED;
     }
     if (plan->dev.r1 == 32) {
         if (iv) rc = sp ? launch_w<32, true, true>(plan, a, stream) : launch_w<32, true, false>(plan, a, stream);

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kGccWarps * 32, 1) gcc_phat_kernel(PlanDev p, 
         const long long len = a.lengths ? a.lengths[b] : a.n_samples;
         const bool valid = (long long)t < 1 + len / p.hop;
         const long long start = valid ? (long long)t * p.hop - F::HALF : 0;
-        const float* x = a.audio + (long long)b * a.clip_stride;
+        const float* x = reinterpret_cast<const float*>(a.audio) + (long long)b * a.clip_stride;
         float* out_row = a.out + (((long long)b * a.T_out + t) * a.C_out + a.c_off) * p.n_mels;
 
         // ---- forward FFTs -> unit phasors ----
@@ -200,6 +200,12 @@ __global__ void __launch_bounds__(kGccWarps * 32, 1) gcc_phat_kernel(PlanDev p, 
     }
 }
 
+int configure_gcc_kernels(const seld_plan* plan) {
+    (void)plan;
+    SELD_CUDA_TRY(cudaFuncSetAttribute(gcc_phat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+    return SELD_OK;
+}
+
 int launch_gcc(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
     if (plan->dev.r1 != 32) {
         set_error("GCC-PHAT is implemented for n_fft = 1024 only");
@@ -208,7 +214,6 @@ int launch_gcc(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
     const int NB = plan->dev.n_bins;
     const size_t smem = sizeof(float) * plan->dev.n_fft + sizeof(float2) * 32 * 32 +
                         (size_t)kGccWarps * (2 * NB + (WarpFft<32>::T_FLOAT2 + 1) / 2) * sizeof(float4);
-    SELD_CUDA_TRY(cudaFuncSetAttribute(gcc_phat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FeatArgs g = a;
     g.G = 1;
     g.n_items = (long long)a.B * a.T_out;

@@ -57,9 +57,12 @@ __global__ void labels_paint_kernel(float* __restrict__ out, long long rows, int
                                     const int4* __restrict__ events, const double2* __restrict__ centres,
                                     double two_s_az, double two_s_el, int pass) {
     const int4 ev = events[blockIdx.x];  // {row0, row1, cls, cell}
-    const long long row0 = ev.x, row1 = ev.y;
+    // a malformed table must not write outside the label tensor: rows are clamped, events with a class or cell out
+    // of range (or a region event without centres) are skipped
+    const long long row0 = ev.x < 0 ? 0 : ev.x, row1 = ev.y > rows ? rows : ev.y;
     if (row1 <= row0) return;
     const int cells = I * J;
+    if (ev.z < 0 || ev.z >= M || ev.w >= cells || (ev.w < 0 && centres == nullptr)) return;
     const int col = pass == 0 ? M - 1 : ev.z;
     const float val = pass == 0 ? 0.f : 1.f;
     if (ev.w >= 0) {

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import threading
 
 import torch
@@ -60,6 +61,7 @@ class FeaturePlan:
                                                self.window.data_ptr(), self.fb.data_ptr()), "seld_plan_create")
         self._handle = handle
         self.device = torch.device("cuda", dev_index)
+        self.fast = bool(_lib.lib().seld_plan_has_fast_path(handle))  # reference filterbank -> fast kernel for C == 4
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -78,12 +80,21 @@ class FeaturePlan:
 
     def run(self, audio: torch.Tensor, mode="logmel", lengths: torch.Tensor | None = None, out: torch.Tensor | None = None,
             c_off: int = 0, stats: torch.Tensor | None = None, stat_frames: torch.Tensor | None = None,
-            spec: torch.Tensor | None = None, T_out: int | None = None, isolate_channels: bool = False) -> torch.Tensor:
-        """audio (B, C, N) float32 CUDA (any strides with unit sample stride) -> (B, T_out, C_out, n_mels).
+            spec: torch.Tensor | None = None, T_out: int | None = None, isolate_channels: bool = False,
+            mean: torch.Tensor | None = None, inv_std: torch.Tensor | None = None, layout: str = "tcf",
+            out_dtype: torch.dtype = torch.float32, check: bool | None = None) -> torch.Tensor:
+        """audio (B, C, N) float32 — or int16 PCM, converted as x / 32768 inside the kernel — CUDA (any strides with
+        unit sample stride) -> (B, T_out, C_out, n_mels).
 
-        ``isolate_channels`` (log-mel mode only): transform every channel on its own, like the reference does
-        (dataset.py:46-50), instead of two channels per complex FFT.  About 2.5x slower; removes the rounding-noise
-        coupling between paired channels that shows when their levels differ by more than ~45 dB."""
+        ``mean`` / ``inv_std`` (float32 (C_out, n_mels) CUDA): write (x - mean) * inv_std, the scaler apply step fused
+        into the kernel; ``layout="ctf"``: write (B, C_out, T_out, n_mels), what every reference model permutes to first
+        (model_conformer.py:191); ``out_dtype=torch.bfloat16``.  These options and int16 input need the fast path
+        (4 channels, 64 HTK mels).
+        ``check``: after a ragged call (``lengths``), read the device status word back and raise if a clip was too
+        short for reflect padding (len <= n_fft/2; torch.stft raises there).  Default: only when ``lengths`` is given.
+        ``isolate_channels`` (log-mel mode only): transform every channel on its own through the generic kernel.  The
+        default path no longer needs it: channel pairs are level-equalised per frame (block floating point), which
+        removes the rounding-noise coupling between a loud and a quiet channel of one packed FFT."""
         mode = MODES[mode] if isinstance(mode, str) else int(mode)
         if isolate_channels:
             if mode != SELD_MODE_LOGMEL or spec is not None:
@@ -94,43 +105,79 @@ class FeaturePlan:
             if out is None:
                 out = torch.empty((audio.shape[0], T_out, c_off + Cn, self.n_mels), dtype=torch.float32, device=self.device)
             for c in range(Cn):  # a one-channel group pairs the channel with an exact zero: nothing can leak into it
-                self.run(audio[:, c:c + 1], mode=mode, lengths=lengths, out=out, c_off=c_off + c, T_out=T_out)
+                self.run(audio[:, c:c + 1], mode=mode, lengths=lengths, out=out, c_off=c_off + c, T_out=T_out, check=check)
             if stats is not None:
                 self.accumulate_stats(out, stats, n_samples=audio.shape[2], lengths=lengths, stat_frames=stat_frames,
                                       c_off=c_off, n_channels=Cn)
             return out
         if audio.dim() != 3:
             raise ValueError("audio must be (B, C, N)")
-        if audio.dtype != torch.float32 or not audio.is_cuda:
-            raise ValueError("audio must be a float32 CUDA tensor")
+        if audio.dtype not in (torch.float32, torch.int16) or not audio.is_cuda:
+            raise ValueError("audio must be a float32 (or int16 PCM) CUDA tensor")
         if audio.device != self.device:
             raise ValueError(f"audio on {audio.device}, plan on {self.device}")
         if audio.stride(2) != 1:
             audio = audio.contiguous()
         B, Cn, N = audio.shape
+        if audio.dtype == torch.int16 and not (self.fast and Cn == 4 and spec is None and mode != SELD_MODE_LOGMEL_GCC):
+            # outside the fast path the kernels take float32: convert on the device first (x / 32768)
+            f32 = torch.empty((B, Cn, N), dtype=torch.float32, device=self.device)
+            src = audio.contiguous()
+            _lib.check(_lib.lib().seld_pcm16_to_float(src.data_ptr(), f32.data_ptr(), src.numel(),
+                                                      torch.cuda.current_stream(self.device).cuda_stream), "seld_pcm16_to_float")
+            audio = f32
         if T_out is None:
             T_out = self.num_frames(N)
         n_out = self.out_channels(mode, Cn)
+        if layout not in ("tcf", "ctf"):
+            raise ValueError("layout must be 'tcf' (B, T, C, F) or 'ctf' (B, C, T, F)")
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+        ctf = layout == "ctf"
         if out is None:
-            out = torch.empty((B, T_out, c_off + n_out, self.n_mels), dtype=torch.float32, device=self.device)
-        if (out.dtype != torch.float32 or not out.is_contiguous() or out.dim() != 4 or out.shape[0] != B
-                or out.shape[1] != T_out or out.shape[3] != self.n_mels or out.device != self.device):
-            raise ValueError("out must be a contiguous float32 (B, T_out, C_out, n_mels) tensor on the plan's device")
+            shape = (B, c_off + n_out, T_out, self.n_mels) if ctf else (B, T_out, c_off + n_out, self.n_mels)
+            out = torch.empty(shape, dtype=out_dtype, device=self.device)
+        t_axis, c_axis = (2, 1) if ctf else (1, 2)
+        if (out.dtype != out_dtype or not out.is_contiguous() or out.dim() != 4 or out.shape[0] != B
+                or out.shape[t_axis] != T_out or out.shape[3] != self.n_mels or out.device != self.device):
+            raise ValueError(f"out must be a contiguous {out_dtype} (B, T_out, C_out, n_mels) tensor ('ctf': (B, C_out, T_out, "
+                             "n_mels)) on the plan's device")
+        C_out = out.shape[c_axis]
+        if (mean is None) != (inv_std is None):
+            raise ValueError("mean and inv_std go together")
         for name, t, dt in (("lengths", lengths, torch.int64), ("stats", stats, torch.float64),
-                            ("stat_frames", stat_frames, torch.int32), ("spec", spec, torch.complex64)):
+                            ("stat_frames", stat_frames, torch.int32), ("spec", spec, torch.complex64),
+                            ("mean", mean, torch.float32), ("inv_std", inv_std, torch.float32)):
             if t is not None and (t.dtype != dt or not t.is_contiguous() or t.device != self.device):
                 raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
-        if stats is not None and stats.numel() != 2 * out.shape[2] * self.n_mels:
+        if stats is not None and stats.numel() != 2 * C_out * self.n_mels:
             raise ValueError("stats must hold 2 * C_out * n_mels float64 values")
+        if mean is not None and (mean.numel() != C_out * self.n_mels or inv_std.numel() != C_out * self.n_mels):
+            raise ValueError("mean / inv_std must hold C_out * n_mels float32 values")
         if spec is not None and tuple(spec.shape) != (B, Cn, T_out, self.n_fft // 2 + 1):
             raise ValueError("spec must be (B, C, T_out, n_fft//2+1) complex64")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().seld_features(
-                self._handle, mode, audio.data_ptr(), audio.stride(0), audio.stride(1), N, _lib.ptr(lengths), B, Cn,
-                out.data_ptr(), T_out, out.shape[2], c_off, _lib.ptr(stats), _lib.ptr(stat_frames), _lib.ptr(spec),
-                stream), "seld_features")
+        opts = None
+        if audio.dtype == torch.int16 or ctf or out_dtype != torch.float32 or mean is not None:
+            opts = _lib.FeatOpts(_lib.SELD_DTYPE_I16 if audio.dtype == torch.int16 else _lib.SELD_DTYPE_F32,
+                                 _lib.SELD_LAYOUT_CTF if ctf else _lib.SELD_LAYOUT_TCF,
+                                 _lib.SELD_DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.SELD_DTYPE_F32,
+                                 _lib.ptr(mean), _lib.ptr(inv_std))
+        # (no torch.cuda.device guard needed: every ABI entry point runs on its plan's device and restores the caller's)
+        _lib.check(_lib.lib().seld_features_ex(
+            self._handle, mode, audio.data_ptr(), audio.stride(0), audio.stride(1), N, _lib.ptr(lengths), B, Cn,
+            out.data_ptr(), T_out, C_out, c_off, _lib.ptr(stats), _lib.ptr(stat_frames), _lib.ptr(spec),
+            ctypes.byref(opts) if opts is not None else None, stream), "seld_features")
+        if check or (check is None and lengths is not None):
+            self.check_status()
         return out
+
+    def check_status(self) -> None:
+        """Synchronise the current stream and raise ``SeldError`` if a kernel flagged a clip as too short for reflect
+        padding (``seld_plan_status``)."""
+        st = ctypes.c_int(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().seld_plan_status(self._handle, stream, ctypes.byref(st)), "seld_plan_status")
 
 
     def accumulate_stats(self, feats: torch.Tensor, stats: torch.Tensor, n_samples: int = 0,
@@ -146,10 +193,9 @@ class FeaturePlan:
         if stat_frames is None and lengths is None and n_samples <= 0:
             raise ValueError("give stat_frames, lengths or n_samples")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().seld_feature_stats(
-                self._handle, feats.data_ptr(), B, T_out, C_out, c_off, C_out - c_off if n_channels is None else n_channels,
-                int(n_samples), _lib.ptr(lengths), _lib.ptr(stat_frames), stats.data_ptr(), stream), "seld_feature_stats")
+        _lib.check(_lib.lib().seld_feature_stats(
+            self._handle, feats.data_ptr(), B, T_out, C_out, c_off, C_out - c_off if n_channels is None else n_channels,
+            int(n_samples), _lib.ptr(lengths), _lib.ptr(stat_frames), stats.data_ptr(), stream), "seld_feature_stats")
         return stats
 
 
@@ -161,7 +207,9 @@ def get_plan(n_fft: int, hop: int, n_mels: int, sample_rate: int, device=None) -
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if device.type == "cuda" and device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    key = (int(n_fft), int(hop), int(n_mels), int(sample_rate), str(device))
+    # the library reads its A/B switches once per plan (seld_plan_create): a changed switch means a new plan
+    key = (int(n_fft), int(hop), int(n_mels), int(sample_rate), str(device), os.environ.get("SELD_FEAT_IMPL", ""),
+           os.environ.get("SELD_V3_CFG", ""))
     with _plans_lock:
         p = _plans.get(key)
         if p is None:
@@ -207,8 +255,8 @@ def audio_to_mel_spectrogram(waveform: torch.Tensor, sample_rate: int, n_fft=Non
 
 def extract_features_host(audio_host: torch.Tensor, out_host: torch.Tensor, plan: FeaturePlan, mode="logmel",
                           chunk: int = 16, n_streams: int = 3) -> torch.Tensor:
-    """End-to-end path for HOST buffers: (B, C, N) float32 — or int16 PCM, converted on the device as x / 32768 like
-    torchaudio.load does for 16-bit WAV (reference dataset.py:18-25) — (ideally pinned) -> out_host
+    """End-to-end path for HOST buffers: (B, C, N) float32 — or int16 PCM, converted as x / 32768 inside the feature
+    kernel's loads like torchaudio.load does for 16-bit WAV (reference dataset.py:18-25) — (ideally pinned) -> out_host
     (B, T, C_out, n_mels).
 
     Clips are streamed through the GPU in chunks on ``n_streams`` CUDA streams so that the host->device
@@ -229,8 +277,9 @@ def extract_features_host(audio_host: torch.Tensor, out_host: torch.Tensor, plan
     cache = plan.__dict__.setdefault("_host_pipes", {})
     pipe = cache.get(key)
     if pipe is None:
+        direct = pcm and plan.fast and Cn == 4 and m != SELD_MODE_LOGMEL_GCC  # the fast kernel loads int16 itself
         pipe = cache[key] = [(torch.cuda.Stream(plan.device),
-                              torch.empty((chunk, Cn, N), dtype=torch.float32, device=plan.device),
+                              None if direct else torch.empty((chunk, Cn, N), dtype=torch.float32, device=plan.device),
                               torch.empty((chunk, T, n_out, plan.n_mels), dtype=torch.float32, device=plan.device),
                               torch.empty((chunk, Cn, N), dtype=torch.int16, device=plan.device) if pcm else None)
                              for _ in range(n_streams)]
@@ -243,11 +292,14 @@ def extract_features_host(audio_host: torch.Tensor, out_host: torch.Tensor, plan
         with torch.cuda.stream(s):
             if pcm:
                 d_pcm[:nb].copy_(audio_host[b0:b0 + nb], non_blocking=True)
-                _lib.check(_lib.lib().seld_pcm16_to_float(d_pcm.data_ptr(), d_in.data_ptr(), nb * Cn * N, s.cuda_stream),
-                           "seld_pcm16_to_float")
+                if d_in is not None:  # configurations outside the fast path: separate conversion pass
+                    _lib.check(_lib.lib().seld_pcm16_to_float(d_pcm.data_ptr(), d_in.data_ptr(), nb * Cn * N, s.cuda_stream),
+                               "seld_pcm16_to_float")
+                src = d_pcm if d_in is None else d_in
             else:
                 d_in[:nb].copy_(audio_host[b0:b0 + nb], non_blocking=True)
-            plan.run(d_in[:nb], mode=m, out=d_out[:nb])
+                src = d_in
+            plan.run(src[:nb], mode=m, out=d_out[:nb])
             out_host[b0:b0 + nb].copy_(d_out[:nb], non_blocking=True)
     for s, *_ in pipe:
         s.synchronize()

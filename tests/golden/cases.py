@@ -28,7 +28,16 @@ AUDIO_CASES = {
     "sine_1k_1e-4_ch0": ("sine", 12000, 0),
     "int16_noise": ("int16", 12000, 21),
     "loud_noise": ("loud", 9600, 22),
+    # unequal channel levels (round 2): the reference transforms every channel on its own (dataset.py:46-50), a
+    # kernel that packs two channels per complex FFT must not let the loud one's rounding noise into the quiet one
+    "level_60db": ("level60", 12000, 23),     # channels 0 and 3 are 60 dB below their FFT partners 1 and 2
+    "level_80db": ("level80", 12000, 24),     # channels 1 and 2 are 80 dB below their partners 0 and 3
+    "level_100db": ("level100", 9600, 25),    # channel 0: -100 dB, channel 2: -40 dB
+    "level_ramp": ("ramp", 24000, 26),        # channel 1 fades from 0 dB to -100 dB over the clip, channel 3 fades in
 }
+# BASELINE.json configs[0]: one 60 s clip; the golden keeps every CONFIG0_STRIDE-th frame of the reference's output
+CONFIG0 = ("noise", SR * 60, 1234)
+CONFIG0_STRIDE = 37
 N_FFTS = (1024, 960)
 
 
@@ -49,6 +58,15 @@ def make_audio(kind: str, n: int, seed: int, channels: int = 4) -> np.ndarray:
     elif kind == "sine":
         x = np.zeros((channels, n))
         x[0] = 1e-4 * np.sin(2 * np.pi * 1000.0 * np.arange(n) / SR)
+    elif kind in ("level60", "level80", "level100"):
+        x = 0.2 * rng.standard_normal((channels, n))
+        gains = {"level60": (1e-3, 1.0, 1.0, 1e-3), "level80": (1.0, 1e-4, 1e-4, 1.0), "level100": (1e-5, 1.0, 1e-2, 1.0)}[kind]
+        x *= np.asarray(gains)[:channels, None]
+    elif kind == "ramp":
+        x = 0.2 * rng.standard_normal((channels, n))
+        fade = 10.0 ** (-5.0 * np.arange(n) / n)  # 0 dB -> -100 dB
+        x[1] *= fade
+        x[3] *= fade[::-1]
     elif kind == "int16":
         x = np.round(np.clip(0.1 * rng.standard_normal((channels, n)), -1, 1) * 32767.0) / 32768.0
     else:

@@ -65,6 +65,15 @@ def main():
                                                  hop_length=cases.HOP, n_mels=cases.N_MELS)
             assert y.dtype == torch.float32 and y.shape == (4, 64, 1 + n // cases.HOP)
             out[f"{name}/logmel_{n_fft}"] = y.numpy()
+    # BASELINE configs[0]: one 60 s 4-channel clip through the reference; every CONFIG0_STRIDE-th frame is kept
+    kind, n, seed = cases.CONFIG0
+    x = cases.make_audio(kind, n, seed)
+    out["config0/sha"] = np.frombuffer(cases.sha(x).encode(), dtype=np.uint8)
+    for n_fft in cases.N_FFTS:
+        y = dataset.audio_to_mel_spectrogram(torch.from_numpy(x), cases.SR, n_fft=n_fft, hop_length=cases.HOP,
+                                             n_mels=cases.N_MELS)
+        assert y.shape == (4, 64, 1 + n // cases.HOP)
+        out[f"config0/logmel_{n_fft}_strided"] = y.numpy()[:, :, ::cases.CONFIG0_STRIDE].copy()
     # channel counts other than 4 (the reference only warns in load_audio)
     for ch in (1, 2, 3, 6):
         x = cases.make_audio("noise", 4800, 100 + ch, channels=ch)

@@ -141,6 +141,21 @@ def test_full_size_clip_config0(sb):
     assert np.abs(y[:, 4:] - want[:, 4:]).max() <= TOL_REL * np.abs(want[:, 4:]).max()
 
 
+@pytest.mark.parametrize("n_fft", cases.N_FFTS)
+def test_full_size_clip_config0_vs_reference_golden(sb, golden_features, n_fft):
+    """BASELINE.json configs[0] pinned to the REFERENCE (not only to the oracle): the golden file keeps every
+    CONFIG0_STRIDE-th frame of dataset.audio_to_mel_spectrogram's output for the 60 s clip."""
+    kind, n, seed = cases.CONFIG0
+    x = cases.make_audio(kind, n, seed)
+    assert cases.sha(x) == bytes(golden_features["config0/sha"]).decode()
+    y = sb.audio_to_mel_spectrogram(torch.from_numpy(x), cases.SR, n_fft=n_fft, hop_length=480, n_mels=64)
+    assert y.shape == (4, 64, 3001)
+    ref = golden_features[f"config0/logmel_{n_fft}_strided"]
+    assert np.abs(y.numpy()[:, :, ::cases.CONFIG0_STRIDE] - ref).max() <= TOL_DB
+    yi = _run(sb, x, n_fft, mode="logmel_iv")[0]  # the 7-channel mode's log-mel channels are the same numbers
+    assert np.abs(yi[::cases.CONFIG0_STRIDE, :4].transpose(1, 2, 0) - ref).max() <= TOL_DB
+
+
 def test_errors_are_exceptions(sb):
     with pytest.raises(sb.SeldError):
         sb.extract_features(torch.zeros(1, 4, 100, device="cuda"), 24000, 1024, 480, 64)  # N <= n_fft/2
