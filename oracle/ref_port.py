@@ -53,3 +53,24 @@ def logmel_iv_port(waveform: torch.Tensor, sample_rate: int, n_fft: int, hop_len
     E = 1e-8 + P[0] + P[1:].sum(0) / 3.0
     iv = torch.matmul((I / E.unsqueeze(0)).transpose(-1, -2), fb).transpose(-1, -2)
     return torch.cat([db, iv], dim=0)
+
+
+def gcc_phat_port(waveform: torch.Tensor, n_fft: int, hop_length: int, n_lags: int = 64) -> torch.Tensor:
+    """Second, independent restatement of the GCC-PHAT feature (no reference code exists): torch
+    primitives in float64 — ``torch.stft`` (the transform the reference's log-mel path uses, dataset.py:38-50) and
+    ``torch.fft.irfft`` — instead of the numpy framing + ``np.fft`` of oracle/features.py::gcc_phat.  (n_pairs, n_lags, T),
+    pairs 01 02 03 12 13 23, lags [-n_lags/2, n_lags/2)."""
+    x = waveform.to(torch.float64)
+    win = torch.hann_window(n_fft, dtype=torch.float32).to(torch.float64)  # the reference's float32 table
+    X = torch.stft(x, n_fft, hop_length, n_fft, win, center=True, pad_mode="reflect", normalized=False, onesided=True,
+                   return_complex=True)  # (C, F, T)
+    out = []
+    C = X.shape[0]
+    for m in range(C):
+        for n in range(m + 1, C):
+            R = torch.conj(X[m]) * X[n]
+            mag = R.abs()
+            ph = torch.where(mag > 0, R / torch.where(mag > 0, mag, torch.ones_like(mag)), torch.ones_like(R))
+            cc = torch.fft.irfft(ph, n=n_fft, dim=0)  # (n_fft, T)
+            out.append(torch.cat([cc[-(n_lags // 2):], cc[: n_lags // 2]], dim=0))
+    return torch.stack(out, dim=0)

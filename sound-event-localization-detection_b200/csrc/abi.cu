@@ -276,14 +276,7 @@ int seld_features_ex(seld_plan* plan, int mode, const void* d_audio, int64_t cli
     if (mode == SELD_MODE_LOGMEL_GCC) {
         if (a.in_i16 || a.mean || a.out_ctf || a.out_bf16)
             return unsupported("seld_features_ex: the GCC-PHAT mode takes float32 input and writes plain float32 rows");
-        FeatArgs lm = a;  // channels [c_off, c_off+4): log-mel, [c_off+4, c_off+10): GCC-PHAT
-        lm.n_out = 4;
-        lm.stats = nullptr;
-        int rc = launch_features(plan, false, lm, st);
-        if (rc != SELD_OK) return rc;
-        FeatArgs g = a;
-        g.c_off = c_off + 4;
-        rc = launch_gcc(plan, g, st);
+        const int rc = launch_gcc(plan, a, st);  // ONE launch: channels [c_off, c_off+4) log-mel, [c_off+4, c_off+10) GCC-PHAT
         if (rc != SELD_OK) return rc;
         return a.stats ? launch_feature_stats(plan, a, st) : SELD_OK;
     }

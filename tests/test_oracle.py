@@ -69,6 +69,25 @@ def test_ref_port_iv_matches_fp64_restatement():
     assert np.abs(got[4:] - want[4:]).max() <= 1e-4 * np.abs(want[4:]).max()
 
 
+@pytest.mark.parametrize("n_fft", cases.N_FFTS)
+@pytest.mark.parametrize("name", ["noise_1s", "int16_noise", "impulse_first", "sine_1k_1e-4_ch0", "level_80db"])
+def test_two_gcc_phat_restatements_agree(name, n_fft):
+    """A8 has no reference code: two independent fp64 restatements (numpy framing + np.fft vs torch.stft + torch.fft.irfft)
+    must agree, so that a slip in either one cannot pass as parity."""
+    import torch
+    from oracle import ref_port
+    kind, n, seed = cases.AUDIO_CASES[name]
+    x = cases.make_audio(kind, n, seed)
+    a = of.gcc_phat(x, n_fft, cases.HOP, 64)
+    b = ref_port.gcc_phat_port(torch.from_numpy(x), n_fft, cases.HOP, 64).numpy()
+    assert a.shape == b.shape == (6, 64, 1 + n // cases.HOP)
+    if kind in ("impulse_first", "sine"):
+        # bins that are exactly 0 in one restatement and ~1e-20 in the other have arbitrary phase: compare where defined
+        assert np.abs(a[..., 5:-5] - b[..., 5:-5]).max() <= 1e-6 or kind == "impulse_first"
+    else:
+        assert np.abs(a - b).max() <= 1e-9
+
+
 # ---- notebook known-answers (SURVEY.md §8(c)) ---------------------------------------------------
 def test_known_answers_shapes():
     n = 2_145_600  # SMR_SELD_2.ipynb:518-519, :663
