@@ -231,11 +231,9 @@ def run_aux(args):
         "cpu_baseline": None, "e2e": None, "gpu_launches": launches * args.steps, "clocks": clocks}))
 
 
-def run_loader(args, dev, peak, peak_src):
-    """configs[4] front-end part: per training batch of 16 windows x 250 frames, features (16, 250, 7, 64) gathered
-    and Gaussian-region label targets (16, 250, 648, 14) painted on the device from compact event tables
-    (SELDDataset(resident='cuda', labels='compact') + DeviceLoader); metric = batches per second of the front-end
-    alone, reported in clip-seconds (16 windows x 5 s per batch)."""
+def _synthetic_dataset(dev, n_files=16, seed=0):
+    """n_files x 60 s synthetic FOA clips + STARSS-style CSVs (3 moving sources each) -> SELDDataset resident in HBM with
+    compact labels (Gaussian-region targets painted per batch) — BASELINE configs[4]'s front-end."""
     import tempfile
 
     import numpy as np
@@ -243,11 +241,11 @@ def run_loader(args, dev, peak, peak_src):
 
     import seld_b200
 
-    n_files, N = 16, SR * CLIP_SECONDS
+    N = SR * CLIP_SECONDS
     tmp = tempfile.mkdtemp(prefix="seld_bench_")
-    rng = np.random.default_rng(0)
+    rng = np.random.default_rng(seed)
     csvs = []
-    for i in range(n_files):  # STARSS-style rows: frame(100 ms), class, source, azimuth, elevation
+    for i in range(n_files):  # rows: frame(100 ms), class, source, azimuth, elevation
         rows = []
         for src in range(3):
             az, el, cls = rng.integers(-180, 180), rng.integers(-60, 60), rng.integers(0, 13)
@@ -258,27 +256,151 @@ def run_loader(args, dev, peak, peak_src):
         with open(path, "w") as fh:
             fh.writelines(",".join(str(int(v)) for v in r) + "\n" for r in rows)
         csvs.append(path)
-    gen = torch.Generator().manual_seed(1234)
+    gen = torch.Generator().manual_seed(1234 + seed)
 
     def loader(path):
         return 0.1 * torch.randn(CH, N, generator=gen), SR
 
-    np.random.seed(42)
-    ds = seld_b200.SELDDataset([f"synthetic://{i}" for i in range(n_files)], csvs, use_gaussian_augmentation=True,
-                               resident="cuda", labels="compact", feature_type="foa_iv", audio_loader=loader, device=dev)
+    np.random.seed(42 + seed)
+    return seld_b200.SELDDataset([f"synthetic://{i}" for i in range(n_files)], csvs, use_gaussian_augmentation=True,
+                                 resident="cuda", labels="compact", feature_type="foa_iv", audio_loader=loader, device=dev)
+
+
+def run_train_step(args):
+    """BASELINE configs[4]: the on-device front-end (features resident in HBM, batch = 16 windows x 250 frames gathered and
+    Gaussian-region targets painted per batch, one launch) feeding the reference's own SELD_Conformer(n_channels=7)
+    training step (trainer.py:165-179: forward, SMRSELDLoss, backward, Adam step, loss.item()), one process per GPU
+    (DistributedDataParallel over NCCL when N > 1).  The model and loss are the reference's files, staged — never
+    committed — under baseline/_ref/ by __graft_entry__.build().  Reports front-end ms, model ms and the fraction."""
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def emit(line):
+        if rank == 0:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            print(json.dumps(line), flush=True)
+            os.dup2(2, 1)
+
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "model_conformer.py")):
+        return emit({"metric": "train_steps_per_sec", "workload": "train_step",
+                     "unavailable": "baseline/_ref/model_conformer.py is not staged (run __graft_entry__.build() where /root/reference exists)"})
+    sys.path.insert(0, ref_dir)
+    from loss import SMRSELDLoss  # reference loss.py:6
+    from model_conformer import SELD_Conformer  # reference model_conformer.py:116
+
+    import seld_b200
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ds = _synthetic_dataset(dev, n_files=16, seed=rank)  # every rank owns its shard of clips
+    dl = seld_b200.DeviceLoader(ds, batch_size=16, shuffle=True, drop_last=True, generator=torch.Generator().manual_seed(rank))
+    torch.manual_seed(0)
+    model = SELD_Conformer(n_channels=7, n_mels=N_MELS, grid_size=(ds.I, ds.J), num_classes=14).to(dev)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    criterion = SMRSELDLoss(loss_type="mse", grid_size=(ds.I, ds.J))  # config.py:71 LOSS_TYPE = 'mse'
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model.train()
+
+    def train_step(spec, lab):  # trainer.py:170-179
+        optimizer.zero_grad()
+        pred = model(spec)
+        loss, _ = criterion(pred, lab)
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    it = iter(dl)
+    def next_batch():
+        nonlocal it
+        try:
+            return next(it)
+        except StopIteration:
+            it = iter(dl)
+            return next(it)
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(*next_batch()).item()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ev[i][0].record()
+        spec, lab = next_batch()       # front-end: one launch (gather + fill + paint) into the ring buffer
+        ev[i][1].record()
+        loss = train_step(spec, lab)   # the reference's model step
+        ev[i][2].record()
+        lv = loss.item()               # trainer.py:182 reads the loss every step
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    clocks = sampler.stop()
+    fe = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    md = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    if world > 1:
+        t = torch.tensor([el, fe, md], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el, fe, md = (float(v) for v in t.tolist())
+    line = {
+        "metric": "train_steps_per_sec", "value": world * steps / el, "unit": "steps/s (global batch = 16 windows x n_gpus)",
+        "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * el / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[4]: on-device front-end (features + Gaussian label targets per batch of 16 windows x "
+                               "250 frames) feeding the reference SELD_Conformer(n_channels=7) train step, 16 x 60 s clips per GPU",
+                   "model": "reference model_conformer.SELD_Conformer + loss.SMRSELDLoss('mse') + Adam (staged in baseline/_ref, fp32)",
+                   "parallelism": f"ddp{world}" if world > 1 else "single GPU", "timing": "wall clock; per-part CUDA events"},
+        "frontend_ms_per_step": fe, "model_ms_per_step": md, "frontend_fraction_of_step": fe / (fe + md),
+        "reference_frontend_bytes_h2d_per_step": 16 * 250 * (7 * 64 + 648 * 14) * 4, "last_loss": lv,
+        "gpu_launches": steps, "clocks": clocks,
+    }
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_loader(args, dev, peak, peak_src):
+    """configs[4] front-end part: per training batch of 16 windows x 250 frames, features (16, 250, 7, 64) gathered
+    and Gaussian-region label targets (16, 250, 648, 14) painted on the device from compact event tables
+    (SELDDataset(resident='cuda', labels='compact') + DeviceLoader); metric = batches per second of the front-end
+    alone, reported in clip-seconds (16 windows x 5 s per batch)."""
+    import torch
+
+    import seld_b200
+
+    n_files = 16
+    ds = _synthetic_dataset(dev, n_files=n_files, seed=0)
     dl = seld_b200.DeviceLoader(ds, batch_size=16, shuffle=True, generator=torch.Generator().manual_seed(0))
     for _ in dl:  # warm-up epoch
         pass
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0, nb, chk = time.perf_counter(), 0, 0.0
-    for _ in range(max(1, args.steps // 10)):
+    e0.record()
+    for _ in range(max(1, args.steps // 2)):
         for spec, lab in dl:
             nb += 1
+    e1.record()
     chk = float(lab[0, 0, 0, 13]) + float(spec[0, 0, 0, 0])  # device -> host read of the last batch
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     bytes_batch = 16 * 250 * (7 * 64 + 648 * 14) * 4
     achieved = bytes_batch * nb / el / 1e9
@@ -288,11 +410,12 @@ def run_loader(args, dev, peak, peak_src):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[4] front-end: batch = 16 windows x 250 frames from {n_files} x 60 s clips "
                                f"({len(ds)} windows): features gather + Gaussian-region label painting on device",
-                   "timing": "wall clock around whole epochs incl. host-side batch assembly", "check": chk},
+                   "timing": "wall clock around whole epochs incl. the host side of every batch (one C-ABI call)",
+                   "device_ms_per_batch": dev_ms / nb, "check": chk},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "kernel": "seld::window_gather_kernel + labels_fill + labels_paint",
+                     "peak_source": peak_src, "kernel": "seld::loader_batch_kernel (gather + fill + paint, one launch per batch)",
                      "algorithmic_bytes_per_launch": bytes_batch},
-        "cpu_baseline": None, "e2e": None, "gpu_launches": 4 * nb, "clocks": clocks}))
+        "cpu_baseline": None, "e2e": None, "gpu_launches": nb, "clocks": clocks}))
 
 
 def main():
@@ -307,12 +430,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="foa", choices=["foa", "mic", "logmel", "labels", "loader"],
+    ap.add_argument("--workload", default="foa", choices=["foa", "mic", "logmel", "labels", "loader", "train_step", "corpus"],
                     help="foa = BASELINE configs[1] (default, the contract line); the others are secondary rows")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload != "foa":
+    if args.workload == "train_step":
+        return run_train_step(args)
+    if args.workload != "foa" and args.workload != "corpus":
         return run_aux(args)
 
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 from C (NCCL prints its version there)

@@ -178,6 +178,23 @@ SELD_API int seld_labels_paint(float* d_out, int64_t rows, int I, int J, int n_c
 SELD_API int seld_window_gather(const float* d_src, int64_t rows, int64_t row_len, const int64_t* d_starts, int n_win,
                        int win_len, const float* d_pad_row, float* d_out, void* stream);
 
+/* One training batch assembled on the device in ONE launch: replaces reference dataset.py:267-330
+ * (_create_windows + __getitem__) plus the DataLoader collate and the 145 MB host->device label copy of
+ * trainer.py:167-168.  Everything it reads is resident in HBM; the host passes only the position in the epoch.
+ *   d_feat       : (rows, row_len) float32 concatenated features, frame-major (row_len = C * n_mels)
+ *   d_order      : int32 permutation of the dataset's window indices for this epoch, or NULL (identity)
+ *   first, n_win : the batch is windows d_order[first .. first + n_win)
+ *   d_win_start  : int32[n_windows] first frame of every window (50 k)
+ *   d_win_lo/hi  : int32[n_windows] range of the event table (sorted by first row) that can touch the window
+ *   d_spec_out   : (n_win, win_len, row_len) float32; frames past the end of the corpus are 0 (dataset.py:290-296)
+ *   d_events     : int32 (n_events, 4) {row0, row1, cls, cell} with absolute rows; d_centres: float64 (n_events, 2)
+ *                  for region events (cell < 0), as seld_labels_paint
+ *   d_labels_out : (n_win, win_len, I * J, n_classes) float32 dense targets, or NULL (features only)           */
+SELD_API int seld_loader_batch(const float* d_feat, int64_t rows, int row_len, const int32_t* d_order, int first, int n_win,
+                      const int32_t* d_win_start, const int32_t* d_win_lo, const int32_t* d_win_hi, int win_len,
+                      float* d_spec_out, const int32_t* d_events, const double* d_centres, int I, int J, int n_classes,
+                      double sigma_az, double sigma_el, float* d_labels_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

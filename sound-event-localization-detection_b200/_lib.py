@@ -51,6 +51,9 @@ _SIGS = {
                                     C.c_double, C.c_double, C.c_void_p]),
     "seld_window_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "seld_loader_batch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

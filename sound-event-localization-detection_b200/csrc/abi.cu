@@ -57,6 +57,10 @@ int launch_window_gather(const float* src, long long rows, long long row_len, co
                          int win_len, const float* pad_row, float* out, cudaStream_t st);
 int launch_scaler_apply(float* x, long long rows, int n_feat, const float* mean, const float* inv_std, cudaStream_t st);
 int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st);
+int launch_loader_batch(const float* feat, long long rows, int row_len, const int* order, int first, int n_win,
+                        const int* win_start, const int* win_lo, const int* win_hi, int win_len, float* out_spec,
+                        const int* events, const double* centres, int I, int J, int M, double sigma_az, double sigma_el,
+                        float* out_lab, cudaStream_t st);
 
 }  // namespace seld
 
@@ -357,6 +361,21 @@ int seld_window_gather(const float* d_src, int64_t rows, int64_t row_len, const 
     SELD_GUARD_PTR(d_out, "seld_window_gather");
     return launch_window_gather(d_src, rows, row_len, reinterpret_cast<const long long*>(d_starts), n_win, win_len,
                                 d_pad_row, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int seld_loader_batch(const float* d_feat, int64_t rows, int row_len, const int32_t* d_order, int first, int n_win,
+                      const int32_t* d_win_start, const int32_t* d_win_lo, const int32_t* d_win_hi, int win_len,
+                      float* d_spec_out, const int32_t* d_events, const double* d_centres, int I, int J, int n_classes,
+                      double sigma_az, double sigma_el, float* d_labels_out, void* stream) {
+    if (n_win < 0 || win_len < 0 || rows < 0 || row_len < 1 || first < 0) return bad_arg("seld_loader_batch: bad size");
+    if (n_win == 0 || win_len == 0) return SELD_OK;
+    if (!d_feat || !d_win_start || !d_spec_out) return bad_arg("seld_loader_batch: null pointer");
+    if (d_labels_out && (!d_win_lo || !d_win_hi || I < 1 || J < 1 || n_classes < 1))
+        return bad_arg("seld_loader_batch: labels need the per-window event ranges and the grid size");
+    SELD_GUARD_PTR(d_spec_out, "seld_loader_batch");
+    return launch_loader_batch(d_feat, rows, row_len, d_order, first, n_win, d_win_start, d_win_lo, d_win_hi, win_len,
+                               d_spec_out, d_events, d_centres, I, J, n_classes, sigma_az, sigma_el, d_labels_out,
+                               static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

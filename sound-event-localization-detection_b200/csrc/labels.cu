@@ -230,3 +230,118 @@ int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t
 }
 
 }  // namespace seld
+
+// ---- on-device batch assembly (replaces reference dataset.py:267-330 _create_windows +
+// __getitem__ + the DataLoader collate of main.py:60-74 for one training batch) ------------------------------------
+// ONE launch per batch.  CTA (w, s) owns rows [s * kSliceRows, ...) of window w of the batch:
+//   features: out_spec[w, f, :] = feat[start_w + f, :] (zeros past the end of the corpus, dataset.py:290-296)
+//   labels  : one-hot background over its rows (dataset.py:114-117 / :297-300), __syncthreads, then the events of
+//             the window (a precomputed range [lo, hi) of the table sorted by first row) clipped to its rows:
+//             pass 0 clears the background class, __syncthreads, pass 1 sets the event class (labels_paint_kernel's
+//             order, so a class M-1 event leaves the background at 1 like the reference).
+// Nothing crosses PCIe and the host does no per-window work: the epoch's permutation, the window starts and the
+// per-window event ranges are resident in HBM.
+namespace seld {
+constexpr int kSliceRows = 5;
+
+__global__ void __launch_bounds__(256) loader_batch_kernel(
+    const float4* __restrict__ feat, long long rows, int row_len4, const int* __restrict__ order, int first, int n_win,
+    const int* __restrict__ win_start, const int* __restrict__ win_lo, const int* __restrict__ win_hi, int win_len,
+    float4* __restrict__ out_spec, const int4* __restrict__ events, const double2* __restrict__ centres, int I, int J, int M,
+    double two_s_az, double two_s_el, float* __restrict__ out_lab) {
+    const int w = blockIdx.y, s = blockIdx.x;
+    const int widx = order ? order[first + w] : first + w;
+    const long long start = win_start[widx];
+    const int f0 = s * kSliceRows, f1 = min(win_len, f0 + kSliceRows);
+    if (f0 >= f1) return;
+    const int cells = I * J;
+    // features
+    {
+        const int n4 = (f1 - f0) * row_len4;
+        float4* dst = out_spec + ((long long)w * win_len + f0) * row_len4;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const int f = i / row_len4, j = i - f * row_len4;
+            const long long r = start + f0 + f;
+            dst[i] = r < rows ? __ldg(feat + r * row_len4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (!out_lab) return;
+    // labels: background fill of this slice (the slice starts at a multiple of cells * M floats, so the period-M
+    // pattern starts at phase 0; 16-byte stores need cells * M % 4 == 0, checked by the launcher)
+    float* lab = out_lab + ((long long)w * win_len + f0) * cells * M;
+    {
+        const long long n_vec = (long long)(f1 - f0) * cells * M / 4;
+        float4* lab4 = reinterpret_cast<float4*>(lab);
+        int r = int((4ll * threadIdx.x) % M);
+        const int step = int((4ll * blockDim.x) % M);
+        for (long long i = threadIdx.x; i < n_vec; i += blockDim.x) {
+            int r1 = r + 1; if (r1 >= M) r1 -= M;
+            int r2 = r1 + 1; if (r2 >= M) r2 -= M;
+            int r3 = r2 + 1; if (r3 >= M) r3 -= M;
+            __stcs(lab4 + i, make_float4(r == M - 1 ? 1.f : 0.f, r1 == M - 1 ? 1.f : 0.f, r2 == M - 1 ? 1.f : 0.f,
+                                         r3 == M - 1 ? 1.f : 0.f));
+            r += step; if (r >= M) r -= M;
+        }
+    }
+    const int lo = win_lo[widx], hi = win_hi[widx];
+    const long long g0 = start + f0, g1 = start + f1;  // absolute rows of this slice
+    // events of the window that touch this slice: every thread tests one event of the window's range (one coalesced
+    // load instead of a serial scan) and appends the hits to a short list; chunks of blockDim.x events
+    __shared__ int s_hits[256];
+    __shared__ int s_n;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass)  // pass 0 clears the background class (all events), pass 1 sets the event class
+        for (int base = lo; base < hi; base += blockDim.x) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+            const int e = base + threadIdx.x;
+            if (e < hi) {
+                const int4 ev = events[e];
+                if (min((long long)ev.y, g1) > max((long long)ev.x, g0) && ev.z >= 0 && ev.z < M && ev.w < cells)
+                    s_hits[atomicAdd(&s_n, 1)] = e;
+            }
+            __syncthreads();
+            const int n = s_n;
+            for (int h = 0; h < n; ++h) {
+                const int e2 = s_hits[h];
+                const int4 ev = events[e2];  // {row0, row1, cls, cell}, absolute rows
+                const long long r0 = max((long long)ev.x, g0), r1 = min((long long)ev.y, g1);
+                const int col = pass == 0 ? M - 1 : ev.z;
+                const float val = pass == 0 ? 0.f : 1.f;
+                if (ev.w >= 0) {
+                    for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+                        lab[((r - g0) * cells + ev.w) * M + col] = val;
+                } else if (centres) {
+                    const double2 c = centres[e2];
+                    for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+                        if (!cell_in_region(cell / J, cell % J, I, J, c.x, c.y, two_s_az, two_s_el)) continue;
+                        for (long long r = r0; r < r1; ++r) lab[((r - g0) * cells + cell) * M + col] = val;
+                    }
+                }
+            }
+        }
+}
+
+int launch_loader_batch(const float* feat, long long rows, int row_len, const int* order, int first, int n_win,
+                        const int* win_start, const int* win_lo, const int* win_hi, int win_len, float* out_spec,
+                        const int* events, const double* centres, int I, int J, int M, double sigma_az, double sigma_el,
+                        float* out_lab, cudaStream_t st) {
+    if (n_win == 0 || win_len == 0) return SELD_OK;
+    if (row_len % 4 != 0 || !aligned16(feat) || !aligned16(out_spec)) {
+        set_error("seld_loader_batch: feature rows must be 16-byte aligned multiples of 4 floats");
+        return SELD_ERR_BAD_ARG;
+    }
+    if (out_lab && (((long long)I * J * M) % 4 != 0 || !aligned16(out_lab))) {
+        set_error("seld_loader_batch: I * J * n_classes must be a multiple of 4 and the label buffer 16-byte aligned");
+        return SELD_ERR_BAD_ARG;
+    }
+    dim3 grid((unsigned)((win_len + kSliceRows - 1) / kSliceRows), (unsigned)n_win);
+    loader_batch_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(feat), rows, row_len / 4, order, first, n_win,
+                                              win_start, win_lo, win_hi, win_len, reinterpret_cast<float4*>(out_spec),
+                                              reinterpret_cast<const int4*>(events), reinterpret_cast<const double2*>(centres),
+                                              I, J, M, 2 * sigma_az, 2 * sigma_el, out_lab);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+}  // namespace seld

@@ -67,12 +67,83 @@ def load_files():
     return train_audio_files, train_meta_files, test_audio_files, test_meta_files
 
 
+def shard_window_plan(frames_per_rank, rank: int, window: int, hop: int):
+    """Windows of the GLOBAL concatenation that a rank owns when the files are sharded by rank.
+
+    The reference windows the concatenation of all files (dataset.py:259, :274-314): window g covers global frames
+    [g*hop, g*hop + window) and straddles file — hence shard — boundaries.  Rank r owns the frames [off, off + T_r) and
+    every window that STARTS in them.  Returns ``(off, local_starts, halo, first_window)``: the global offset of the
+    rank's first frame, the owned windows' start frames relative to it, the number of frames past the end of the shard
+    that those windows read from the following ranks (0 for the last non-empty rank: the reference pads there) and the
+    global index of the first owned window."""
+    frames_per_rank = [int(t) for t in frames_per_rank]
+    off, T, total = sum(frames_per_rank[:rank]), frames_per_rank[rank], sum(frames_per_rank)
+    first = -(-off // hop)  # ceil
+    starts = list(range(first * hop, off + T, hop))
+    halo = 0
+    if starts:
+        halo = max(0, min(starts[-1] + window, total) - (off + T))
+    return off, [g - off for g in starts], halo, first
+
+
+def exchange_shard_halo(head: torch.Tensor, head_events: np.ndarray, head_centres, n_frames: int, window: int, hop: int,
+                        group=None):
+    """The neighbour exchange of SURVEY.md §8(e): every rank offers the first ``min(T_r, window)`` frames of its
+    features (``head``, (h, row_len)) with the events that touch them (rows relative to the rank's first frame); one
+    ``all_gather`` of the padded heads (window x row_len floats per rank, ~0.45 MB) and one ``all_gather_object`` of the
+    small event tables give every rank the halo of the following ranks.  Works on any backend (NCCL for CUDA tensors,
+    gloo for CPU tensors in the tests).  Returns ``(plan, halo_feat (halo, row_len), halo_events, halo_centres)`` with the
+    halo events' rows relative to this rank's first frame."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    row_len = head.shape[1]
+    h = head.shape[0]
+    assert h == min(n_frames, window)
+    meta = [None] * world
+    dist.all_gather_object(meta, {"T": int(n_frames), "ev": np.asarray(head_events), "ce": head_centres}, group=group)
+    # (a gloo group moves CUDA tensors through the host; NCCL gathers them in place over NVLink)
+    xdev = torch.device("cpu") if dist.get_backend(group) == "gloo" else head.device
+    padded = torch.zeros((window, row_len), dtype=head.dtype, device=xdev)
+    padded[:h] = head.to(xdev)
+    heads = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(heads, padded, group=group)
+    heads = [t.to(head.device) for t in heads]
+    frames = [m["T"] for m in meta]
+    plan = shard_window_plan(frames, rank, window, hop)
+    halo = plan[2]
+    parts, evs, ces, got, r = [], [], [], 0, rank + 1
+    base = frames[rank]  # local row of the next rank's first frame
+    while got < halo and r < world:
+        take = min(halo - got, min(frames[r], window))
+        if take > 0:
+            parts.append(heads[r][:take])
+            ev = meta[r]["ev"]
+            if len(ev):
+                sel = ev[:, 0] < take
+                e = ev[sel].copy()
+                e[:, 1] = np.minimum(e[:, 1], take)
+                e[:, 0] += base
+                e[:, 1] += base
+                evs.append(e)
+                if meta[r]["ce"] is not None:
+                    ces.append(np.asarray(meta[r]["ce"])[sel])
+        got += take
+        base += frames[r]
+        if frames[r] > window and got < halo:  # cannot happen: a halo is shorter than a window
+            break
+        r += 1
+    halo_feat = torch.cat(parts) if parts else head.new_zeros((0, row_len))
+    halo_events = np.concatenate(evs) if evs else np.zeros((0, 4), np.int32)
+    halo_centres = np.concatenate(ces) if ces else None
+    return plan, halo_feat, halo_events, halo_centres
+
+
 class SELDDataset(Dataset):
     """Reference dataset.py:167-330 (+ smrl_seld_gaussian.py:539-700 for ``use_gaussian_augmentation``)."""
 
     def __init__(self, audio_files, metadata_files, num_classes=14, use_gaussian_augmentation=False, *,
                  device=None, resident="cpu", labels="dense", feature_type=None, audio_loader=None,
-                 compute_stats=False):
+                 compute_stats=False, distributed=False, group=None):
         assert len(audio_files) == len(metadata_files), \
             "Number of audio files must match number of metadata files"
         config = get_config()
@@ -103,6 +174,12 @@ class SELDDataset(Dataset):
         self.device = L._cuda_device(device)
         self._load_audio = audio_loader or load_audio
         self._compute_stats = compute_stats
+        # distributed=True: ``audio_files`` is this rank's contiguous block of the global list (``shard_files``); windows
+        # are those of the GLOBAL concatenation that start in the block, bit-identical to the unsharded dataset's — the
+        # frames they read past the block's end (at most window - 1 = 249) come from the following ranks in one neighbour exchange
+        self._distributed, self._group = bool(distributed), group
+        self.halo_frames, self.global_frame_offset, self.first_window = 0, 0, 0
+        self._window_starts = None
 
         logger.info(f"SELDDataset initialization started...")
         logger.info(f"  Files: {len(audio_files)} audio files")
@@ -179,8 +256,28 @@ class SELDDataset(Dataset):
         self.events = (np.concatenate([p[2] for p in per_file]) if per_file else np.zeros((0, 4), np.int32))
         ce = [p[3] for p in per_file if p[3] is not None]
         self.centres = np.concatenate(ce) if ce else None
+        rows = total
+        if self._distributed:  # windows of the global concatenation: fetch the frames they read from the next ranks
+            W, H = self.window_length_frames, self.hop_length_frames
+            h = min(total, W)
+            ev = self.events
+            sel = ev[:, 0] < h if len(ev) else np.zeros(0, bool)
+            head_ev = ev[sel].copy()
+            if len(head_ev):
+                head_ev[:, 1] = np.minimum(head_ev[:, 1], h)
+            head_ce = self.centres[sel] if self.centres is not None and len(ev) else None
+            plan_, halo_feat, halo_ev, halo_ce = exchange_shard_halo(feats[:h].reshape(h, -1), head_ev, head_ce, total, W, H,
+                                                                   self._group)
+            self.global_frame_offset, self._window_starts, self.halo_frames, self.first_window = plan_
+            if self.halo_frames:
+                feats = torch.cat([feats, halo_feat.view(-1, n_ch, self.n_mels)], dim=0)
+                self.events = np.concatenate([self.events, halo_ev.astype(np.int32)]) if len(halo_ev) else self.events
+                if halo_ce is not None:
+                    self.centres = halo_ce if self.centres is None else np.concatenate([self.centres, halo_ce])
+            rows = total + self.halo_frames
+        self._rows = rows  # frames available to windows: the rank's own + the halo of the following ranks
         if self.label_mode == "dense":
-            lab = torch.empty((total, self.total_cells, self.num_classes), dtype=torch.float32, device=dev)
+            lab = torch.empty((rows, self.total_cells, self.num_classes), dtype=torch.float32, device=dev)
             L.encode_dense(lab, self.events, self.centres, self.I, self.J)
         else:
             lab = None
@@ -205,9 +302,9 @@ class SELDDataset(Dataset):
         """dataset.py:267-317: windows [50k, 50k+250) while 50k < sum T; the tail is padded with 0 features and
         background labels.  Full windows are views, exactly like the reference."""
         self.windows = []
-        W, H, T = self.window_length_frames, self.hop_length_frames, self.total_frames
-        start_frame, window_idx = 0, 0
-        while start_frame < T:
+        W, H, T = self.window_length_frames, self.hop_length_frames, self._rows
+        starts = self._window_starts if self._distributed else range(0, self.total_frames, H)
+        for window_idx, start_frame in enumerate(starts):
             end_frame = start_frame + W
             if end_frame <= T:
                 window_spec = self._features_tcf[start_frame:end_frame]
@@ -227,8 +324,6 @@ class SELDDataset(Dataset):
                     window_labels = None
             self.windows.append({'spectrogram': window_spec, 'labels': window_labels, 'window_idx': window_idx,
                                  'start_frame': start_frame, 'end_frame': min(end_frame, T)})
-            start_frame += H
-            window_idx += 1
         logger.info(f"Created {len(self.windows)} windows")
 
     def __len__(self):
@@ -268,7 +363,7 @@ class SELDDataset(Dataset):
     def paint_label_windows(self, starts, out: torch.Tensor | None = None) -> torch.Tensor:
         """Dense labels (n, W, I*J, M) for windows starting at ``starts``, painted on the GPU from the compact
         event tables (background for frames past the end, like the reference's padding)."""
-        W, T = self.window_length_frames, self.total_frames
+        W, T = self.window_length_frames, self._rows
         n = len(starts)
         if out is None:
             out = torch.empty((n, W, self.total_cells, self.num_classes), dtype=torch.float32, device=self.device)
@@ -328,52 +423,81 @@ def _lib_mode(mode: str) -> int:
 class DeviceLoader:
     """On-device replacement for ``DataLoader(SELDDataset)`` (main.py:60-74 builds one with 2 workers and pinned
     memory; trainer.py only needs ``.dataset``, ``len()`` and iteration — trainer.py:42-47, :165-168).
-    Batches ``(B, 250, C, 64)`` / ``(B, 250, I*J, M)`` are gathered (features) and painted or gathered (labels)
-    in HBM with the window kernels; nothing crosses PCIe per step."""
 
-    def __init__(self, dataset: SELDDataset, batch_size=16, shuffle=False, drop_last=False, generator=None):
+    Everything a batch needs is resident in HBM: the concatenated features, the event table sorted by first row, the
+    start frame and the event range of every window, and the epoch's permutation (uploaded once per epoch).  A batch
+    ``(B, 250, C, 64)`` / ``(B, 250, I*J, M)`` is ONE kernel launch (``seld_loader_batch``: feature gather + background
+    fill + event painting) into a preallocated ring of ``depth`` output buffers — no per-batch host work besides that
+    call, no host->device copy, no synchronisation.  The tensors of a batch are overwritten ``depth`` batches later
+    (the training loop consumes a batch before asking for the next, trainer.py:165-179).
+    ``labels='dense'`` datasets (labels materialised in HBM) gather the label windows instead of painting them."""
+
+    def __init__(self, dataset: SELDDataset, batch_size=16, shuffle=False, drop_last=False, generator=None, depth=3):
         if dataset.resident != "cuda":
             raise ValueError("DeviceLoader needs SELDDataset(resident='cuda')")
-        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, batch_size, shuffle, drop_last
+        self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
         self.generator = generator
-        ds = dataset
-        self._starts = torch.tensor([w['start_frame'] for w in ds.windows], dtype=torch.int64)
+        ds, dev = dataset, dataset.device
+        W = ds.window_length_frames
+        starts = np.asarray([w['start_frame'] for w in ds.windows], dtype=np.int64)
+        self._win_start = torch.from_numpy(starts.astype(np.int32)).to(dev)
+        self._win_start64 = torch.from_numpy(starts).to(dev)
+        self._identity = torch.arange(len(starts), dtype=torch.int32, device=dev)
         row = ds.n_channels * ds.n_mels
-        self._pad_feat = torch.zeros(row, dtype=torch.float32, device=ds.device)
-        pad_lab = torch.zeros((ds.total_cells, ds.num_classes), dtype=torch.float32, device=ds.device)
-        pad_lab[:, ds.num_classes - 1] = 1.0
-        self._pad_lab = pad_lab.reshape(-1)
+        self._ev = self._ce = self._lo = self._hi = None
+        if ds.label_mode == "compact":
+            ev, ce = ds._events_sorted()
+            if len(ev):
+                row0 = ev[:, 0]
+                lo = np.searchsorted(row0, starts - (ds._ev_maxlen - 1), side="left")
+                hi = np.searchsorted(row0, np.minimum(starts + W, ds._rows), side="left")
+            else:
+                lo = hi = np.zeros(len(starts), np.int64)
+            self._lo = torch.from_numpy(lo.astype(np.int32)).to(dev)
+            self._hi = torch.from_numpy(hi.astype(np.int32)).to(dev)
+            self._ev = torch.from_numpy(np.ascontiguousarray(ev, dtype=np.int32)).to(dev) if len(ev) else None
+            self._ce = torch.from_numpy(np.ascontiguousarray(ce, dtype=np.float64)).to(dev) if ce is not None and len(ce) else None
+        else:
+            pad_lab = torch.zeros((ds.total_cells, ds.num_classes), dtype=torch.float32, device=dev)
+            pad_lab[:, ds.num_classes - 1] = 1.0
+            self._pad_lab = pad_lab.reshape(-1)
+        B = self.batch_size
+        self._ring = [(torch.empty((B, W, ds.n_channels, ds.n_mels), dtype=torch.float32, device=dev),
+                       torch.empty((B, W, ds.total_cells, ds.num_classes), dtype=torch.float32, device=dev))
+                      for _ in range(max(2, int(depth)))]
+        self._slot = 0
+        self._args = (ds._features_tcf.data_ptr(), ds._features_tcf.shape[0], row)
 
     def __len__(self):
         n = len(self.dataset)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
-    def _gather(self, src2d: torch.Tensor, starts_dev: torch.Tensor, pad_row: torch.Tensor, n: int) -> torch.Tensor:
-        W = self.dataset.window_length_frames
-        rows, row_len = src2d.shape
-        out = torch.empty((n, W, row_len), dtype=torch.float32, device=src2d.device)
-        stream = torch.cuda.current_stream(src2d.device).cuda_stream
-        _lib.check(_lib.lib().seld_window_gather(src2d.data_ptr(), rows, row_len, starts_dev.data_ptr(), n, W,
-                                                 pad_row.data_ptr(), out.data_ptr(), stream), "seld_window_gather")
-        return out
-
     def __iter__(self):
         ds = self.dataset
-        n = len(ds)
-        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
-        for i in range(0, n, self.batch_size):
-            idx = order[i:i + self.batch_size]
-            if self.drop_last and len(idx) < self.batch_size:
+        n, B, W = len(ds), self.batch_size, ds.window_length_frames
+        if self.shuffle:  # the permutation is drawn like DataLoader's RandomSampler and uploaded once per epoch
+            order = torch.randperm(n, generator=self.generator).to(torch.int32).to(ds.device, non_blocking=True)
+        else:
+            order = self._identity
+        lib, check = _lib.lib(), _lib.check
+        feat_ptr, rows, row = self._args
+        compact = ds.label_mode == "compact"
+        ev_ptr, ce_ptr = _lib.ptr(self._ev), _lib.ptr(self._ce)
+        lo_ptr, hi_ptr = _lib.ptr(self._lo), _lib.ptr(self._hi)
+        order_ptr, start_ptr = order.data_ptr(), self._win_start.data_ptr()
+        stream = torch.cuda.current_stream(ds.device).cuda_stream
+        for first in range(0, n, B):
+            nb = min(B, n - first)
+            if self.drop_last and nb < B:
                 break
-            starts = self._starts[idx]
-            starts_dev = starts.to(ds.device)
-            f = ds._features_tcf
-            spec = self._gather(f.view(f.shape[0], -1), starts_dev, self._pad_feat, len(idx))
-            spec = spec.view(len(idx), ds.window_length_frames, ds.n_channels, ds.n_mels)
-            if ds.label_mode == "dense":
+            spec, lab = self._ring[self._slot]
+            self._slot = (self._slot + 1) % len(self._ring)
+            check(lib.seld_loader_batch(feat_ptr, rows, row, order_ptr, first, nb, start_ptr, lo_ptr, hi_ptr, W, spec.data_ptr(),
+                                        ev_ptr, ce_ptr, ds.I, ds.J, ds.num_classes, 5.0, 5.0,
+                                        lab.data_ptr() if compact else None, stream), "seld_loader_batch")
+            if not compact:  # dense labels resident in HBM: gather their windows
                 l = ds.concatenated_labels
-                lab = self._gather(l.view(l.shape[0], -1), starts_dev, self._pad_lab, len(idx))
-                lab = lab.view(len(idx), ds.window_length_frames, ds.total_cells, ds.num_classes)
-            else:
-                lab = ds.paint_label_windows(starts.tolist())
-            yield spec, lab
+                starts_dev = self._win_start64[order[first:first + nb].long()]
+                check(lib.seld_window_gather(l.data_ptr(), l.shape[0], l.shape[1] * l.shape[2], starts_dev.data_ptr(), nb, W,
+                                             self._pad_lab.data_ptr(), lab.data_ptr(), stream), "seld_window_gather")
+            yield (spec, lab) if nb == B else (spec[:nb], lab[:nb])

@@ -144,6 +144,31 @@ def test_device_loader_matches_dataset_items(sb, label_mode):
     assert k == len(ds)
 
 
+@pytest.mark.parametrize("gaussian", [False, True])
+def test_device_loader_shuffled_one_launch_batches(sb, gaussian):
+    """Shuffled epochs through the one-launch batch kernel (device-side event selection): every batch equals the dense
+    dataset's items of the same permutation, point and Gaussian-region labels, partial last batch, ring reuse."""
+    args = (list(FILES), [cases.csv_path("edges"), cases.csv_path("floatcol")])
+    np.random.seed(7)
+    dense = sb.SELDDataset(*args, use_gaussian_augmentation=gaussian, audio_loader=_fake_loader(FILES), resident="cuda",
+                           feature_type="foa_iv")
+    np.random.seed(7)
+    ds = sb.SELDDataset(*args, use_gaussian_augmentation=gaussian, audio_loader=_fake_loader(FILES), resident="cuda",
+                        labels="compact", feature_type="foa_iv")
+    for bs, drop in ((2, False), (4, True), (16, False)):
+        dl = sb.DeviceLoader(ds, batch_size=bs, shuffle=True, drop_last=drop, generator=torch.Generator().manual_seed(3), depth=2)
+        for epoch in range(2):
+            order = torch.randperm(len(ds), generator=torch.Generator().manual_seed(3)) if epoch == 0 else None
+            seen = 0
+            for bi, (spec, lab) in enumerate(dl):
+                if order is not None:
+                    for i in range(spec.shape[0]):
+                        s_ref, l_ref = dense[int(order[bi * bs + i])]
+                        assert torch.equal(spec[i], s_ref) and torch.equal(lab[i], l_ref)
+                seen += spec.shape[0]
+            assert seen == (len(ds) // bs * bs if drop else len(ds)) and bi + 1 == len(dl)
+
+
 def test_gaussian_dataset_compact_equals_dense(sb):
     args = (list(FILES), [cases.csv_path("edges"), cases.csv_path("floatcol")])
     np.random.seed(5)
@@ -179,3 +204,78 @@ def test_scaler_stats_apply(sb):
     sc.apply(x)
     want = (f - m_ref) / s_ref
     assert np.abs(x.cpu().numpy().reshape(ds.total_frames, -1) - want).max() <= 1e-4
+
+
+# ---- clip sharding with exact global windows (SURVEY.md §8(e) nuance; reference dataset.py:259, :274-314) ----
+SHARD_FILES = {"synthetic://a": ("noise", 97440, 31), "synthetic://b": ("noise", 60000, 32), "synthetic://c": ("noise", 30000, 33),
+               "synthetic://d": ("noise", 72000, 34)}
+SHARD_CSVS = ["edges", "floatcol", "weird", "basic"]
+
+
+def _shard_worker(rank, world, port, label_mode, gaussian, q):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests", "golden")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0 here; NCCL needs one GPU per rank
+    import seld_b200 as sb
+    files, csvs = list(SHARD_FILES), [cases.csv_path(c) for c in SHARD_CSVS]
+    mine_a, mine_m = sb.shard_files(files, csvs, rank, world)
+    np.random.seed(11)  # (rank 0 draws the noise of its files first; the unsharded run below draws all in order)
+    if gaussian and rank == 1:  # consume the draws of rank 0's files so that both runs see the same noise per source
+        from seld_b200 import labels as L
+        for a, m in zip(*sb.shard_files(files, csvs, 0, world)):
+            L.region_events(m, SHARD_FILES[a][1] / 24000, 18, 36, 14)
+    ds = sb.SELDDataset(mine_a, mine_m, use_gaussian_augmentation=gaussian, audio_loader=_fake_loader(SHARD_FILES), resident="cuda",
+                        labels=label_mode, feature_type="foa_iv", distributed=True)
+    # (numpy arrays: pickled by value; torch tensors would travel as file descriptors of a process that has exited)
+    items = [(ds.first_window + k, ds[k][0].cpu().numpy(), np.packbits(ds[k][1].cpu().numpy() != 0)) for k in range(len(ds))]
+    batches = []
+    if label_mode == "compact":
+        for spec, lab in sb.DeviceLoader(ds, batch_size=4):
+            batches.append((spec.cpu().numpy().copy(), np.packbits(lab.cpu().numpy() != 0, axis=None).reshape(spec.shape[0], -1)))
+    q.put((rank, ds.global_frame_offset, ds.halo_frames, items, batches))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("label_mode,gaussian", [("dense", False), ("compact", True)])
+def test_sharded_dataset_windows_equal_the_unsharded_ones(sb, label_mode, gaussian):
+    """Two ranks (two processes, gloo, one GPU): rank r's window g is bit-identical to window g of the dataset built from
+    ALL files in one process — the reference's semantics (windows of the global concatenation straddle file and shard
+    boundaries).  Features, point labels and Gaussian-region labels, through __getitem__ and through DeviceLoader."""
+    import socket
+    import torch.multiprocessing as mp
+    files, csvs = list(SHARD_FILES), [cases.csv_path(c) for c in SHARD_CSVS]
+    np.random.seed(11)
+    full = sb.SELDDataset(files, csvs, use_gaussian_augmentation=gaussian, audio_loader=_fake_loader(SHARD_FILES), resident="cuda",
+                          feature_type="foa_iv")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, label_mode, gaussian, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    seen = []
+    for rank, off, halo, items, batches in res:
+        assert halo <= 249  # a window that starts on the last frames of a shard reads up to window - 1 frames of the next
+        for g, spec, lab_bits in items:
+            s_ref, l_ref = full[g]
+            l_ref = l_ref.cpu().numpy()
+            assert set(np.unique(l_ref).tolist()) <= {0.0, 1.0}
+            assert np.array_equal(spec, s_ref.cpu().numpy()) and np.array_equal(lab_bits, np.packbits(l_ref != 0)), (rank, g)
+            seen.append(g)
+        k = 0
+        for spec, lab_bits in batches:
+            for i in range(spec.shape[0]):
+                assert np.array_equal(spec[i], items[k][1]) and np.array_equal(lab_bits[i], items[k][2])
+                k += 1
+    assert seen == list(range(len(full)))
+    assert res[0][1] == 0 and res[0][2] > 0 and res[1][2] == 0  # rank 0 reads a halo from rank 1; the last rank pads
