@@ -69,6 +69,16 @@ def test_ref_port_iv_matches_fp64_restatement():
     assert np.abs(got[4:] - want[4:]).max() <= 1e-4 * np.abs(want[4:]).max()
 
 
+def test_label_cost_port_equals_reference_golden(golden_labels):
+    """The loop-for-loop label port that bench.py times on the CPU reproduces the reference's output bit for bit."""
+    from oracle import ref_port
+    for name in ("edges", "floatcol"):
+        _csv, n = cases.LABEL_CASES[name]
+        got = ref_port.metadata_to_labels_port(cases.csv_path(name), n / cases.SR).numpy()
+        want = cases.unpack_labels(golden_labels[f"{name}/point_bits"], tuple(golden_labels[f"{name}/shape"]))
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("n_fft", cases.N_FFTS)
 @pytest.mark.parametrize("name", ["noise_1s", "int16_noise", "impulse_first", "sine_1k_1e-4_ch0", "level_80db"])
 def test_two_gcc_phat_restatements_agree(name, n_fft):
