@@ -195,6 +195,28 @@ SELD_API int seld_loader_batch(const float* d_feat, int64_t rows, int row_len, c
                       float* d_spec_out, const int32_t* d_events, const double* d_centres, int I, int J, int n_classes,
                       double sigma_az, double sigma_el, float* d_labels_out, void* stream);
 
+/* Class loss from compact targets (reference loss.py:27-54 SMRSELDLoss.class_mse_loss /
+ * class_ce_loss, which take the dense (B, T, I*J, n_classes) float32 targets — 145 MB per batch, > 99.7 % background).
+ *
+ * seld_batch_class_mask: the targets of one batch as a class-SET mask per (window, frame, cell), uint16 (n_win, win_len,
+ *   I*J): 0 = no event (one-hot background), bit c = an event of class c covers the cell.  Same arguments and event
+ *   selection as seld_loader_batch; 5 MB instead of 145 MB.
+ * seld_class_loss: softmax-MSE (SELD_LOSS_MSE: sum over cells and classes of (softmax(z) - y)^2) or cross entropy
+ *   (SELD_LOSS_CE: sum of w[t] * (logsumexp(z) - z[t]) with t = lowest class of the mask, torch.argmax's choice for a
+ *   multi-hot row, and the sum of w[t]) of d_logits (n_cells, n_classes) float32.
+ *   d_sums      : float64[2], the call ADDS {loss sum, weight sum (CE)}; NULL = backward only
+ *   d_grad      : NULL, or (n_cells, n_classes) float32 <- d(loss sum)/d(logits) * (*d_grad_scale); the scale is a DEVICE
+ *                 float (upstream gradient x the mean's 1/N), so autograd never synchronises
+ *   d_class_weight : float32[n_classes] or NULL (CE only).   n_classes == 14 (the reference's NUM_CLASSES).            */
+#define SELD_LOSS_MSE 0
+#define SELD_LOSS_CE 1
+SELD_API int seld_batch_class_mask(const int32_t* d_order, int first, int n_win, const int32_t* d_win_start,
+                          const int32_t* d_win_lo, const int32_t* d_win_hi, int win_len, const int32_t* d_events,
+                          const double* d_centres, int I, int J, int n_classes, double sigma_az, double sigma_el,
+                          uint16_t* d_mask, void* stream);
+SELD_API int seld_class_loss(int loss_type, const float* d_logits, const uint16_t* d_mask, int64_t n_cells, int n_classes,
+                    const float* d_class_weight, double* d_sums, float* d_grad, const float* d_grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,16 @@ def metadata_to_labels_port(metadata_path, audio_duration, I=18, J=36, num_class
             if cell not in taken:
                 out[t, cell, num_classes - 1] = 1.0
     return out
+
+
+def class_mse_loss_port(y_pred: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+    """loss.py:43-54: softmax over the classes, mean squared error against the dense targets."""
+    return torch.nn.functional.mse_loss(torch.softmax(y_pred, dim=-1), y_true)
+
+
+def class_ce_loss_port(y_pred: torch.Tensor, y_true: torch.Tensor, class_weights: torch.Tensor | None = None) -> torch.Tensor:
+    """loss.py:27-41 with the constructor's ``nn.CrossEntropyLoss(weight=class_weights)`` (loss.py:21-25): targets are
+    the argmax of the dense rows."""
+    M = y_pred.shape[-1]
+    target = torch.argmax(y_true, dim=-1).view(-1)
+    return torch.nn.CrossEntropyLoss(weight=class_weights)(y_pred.reshape(-1, M), target)

@@ -57,6 +57,11 @@ int launch_window_gather(const float* src, long long rows, long long row_len, co
                          int win_len, const float* pad_row, float* out, cudaStream_t st);
 int launch_scaler_apply(float* x, long long rows, int n_feat, const float* mean, const float* inv_std, cudaStream_t st);
 int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t st);
+int launch_batch_class_mask(const int* order, int first, int n_win, const int* win_start, const int* win_lo, const int* win_hi,
+                            int win_len, const int* events, const double* centres, int I, int J, int M, double sigma_az,
+                            double sigma_el, unsigned short* mask, cudaStream_t st);
+int launch_class_loss(int mode, const float* logits, const unsigned short* mask, long long n_cells, int M, const float* weight,
+                      double* sums, float* grad, const float* gscale, cudaStream_t st);
 int launch_loader_batch(const float* feat, long long rows, int row_len, const int* order, int first, int n_win,
                         const int* win_start, const int* win_lo, const int* win_hi, int win_len, float* out_spec,
                         const int* events, const double* centres, int I, int J, int M, double sigma_az, double sigma_el,
@@ -376,6 +381,29 @@ int seld_loader_batch(const float* d_feat, int64_t rows, int row_len, const int3
     return launch_loader_batch(d_feat, rows, row_len, d_order, first, n_win, d_win_start, d_win_lo, d_win_hi, win_len,
                                d_spec_out, d_events, d_centres, I, J, n_classes, sigma_az, sigma_el, d_labels_out,
                                static_cast<cudaStream_t>(stream));
+}
+
+int seld_batch_class_mask(const int32_t* d_order, int first, int n_win, const int32_t* d_win_start, const int32_t* d_win_lo,
+                          const int32_t* d_win_hi, int win_len, const int32_t* d_events, const double* d_centres, int I, int J,
+                          int n_classes, double sigma_az, double sigma_el, uint16_t* d_mask, void* stream) {
+    if (n_win < 0 || win_len < 0 || first < 0 || I < 1 || J < 1 || n_classes < 1) return bad_arg("seld_batch_class_mask: bad size");
+    if (n_win == 0 || win_len == 0) return SELD_OK;
+    if (!d_win_start || !d_win_lo || !d_win_hi || !d_mask) return bad_arg("seld_batch_class_mask: null pointer");
+    SELD_GUARD_PTR(d_mask, "seld_batch_class_mask");
+    return launch_batch_class_mask(d_order, first, n_win, d_win_start, d_win_lo, d_win_hi, win_len, d_events, d_centres, I, J,
+                                   n_classes, sigma_az, sigma_el, d_mask, static_cast<cudaStream_t>(stream));
+}
+
+int seld_class_loss(int loss_type, const float* d_logits, const uint16_t* d_mask, int64_t n_cells, int n_classes,
+                    const float* d_class_weight, double* d_sums, float* d_grad, const float* d_grad_scale, void* stream) {
+    if (loss_type != SELD_LOSS_MSE && loss_type != SELD_LOSS_CE) return bad_arg("seld_class_loss: unknown loss type");
+    if (n_cells < 0 || n_classes < 1) return bad_arg("seld_class_loss: bad size");
+    if (n_cells == 0) return SELD_OK;
+    if (!d_logits || !d_mask || (!d_sums && !d_grad)) return bad_arg("seld_class_loss: null pointer");
+    if (d_grad && !d_grad_scale) return bad_arg("seld_class_loss: d_grad needs d_grad_scale");
+    SELD_GUARD_PTR(d_logits, "seld_class_loss");
+    return launch_class_loss(loss_type, d_logits, d_mask, n_cells, n_classes, d_class_weight, d_sums, d_grad, d_grad_scale,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

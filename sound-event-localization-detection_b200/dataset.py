@@ -432,9 +432,15 @@ class DeviceLoader:
     (the training loop consumes a batch before asking for the next, trainer.py:165-179).
     ``labels='dense'`` datasets (labels materialised in HBM) gather the label windows instead of painting them."""
 
-    def __init__(self, dataset: SELDDataset, batch_size=16, shuffle=False, drop_last=False, generator=None, depth=3):
+    def __init__(self, dataset: SELDDataset, batch_size=16, shuffle=False, drop_last=False, generator=None, depth=3,
+                 targets="dense"):
         if dataset.resident != "cuda":
             raise ValueError("DeviceLoader needs SELDDataset(resident='cuda')")
+        if targets not in ("dense", "mask"):
+            raise ValueError("targets must be 'dense' ((B, 250, I*J, M) float32) or 'mask' ((B, 250, I*J) int16 class sets)")
+        if targets == "mask" and dataset.label_mode != "compact":
+            raise ValueError("targets='mask' needs SELDDataset(labels='compact')")
+        self.targets = targets
         self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
         self.generator = generator
         ds, dev = dataset, dataset.device
@@ -462,8 +468,11 @@ class DeviceLoader:
             pad_lab[:, ds.num_classes - 1] = 1.0
             self._pad_lab = pad_lab.reshape(-1)
         B = self.batch_size
+        # targets='mask' (SURVEY.md §8(f) N4): int16 class sets for seld_b200.loss.CompactSMRSELDLoss instead of dense labels
+        lab_shape, lab_dtype = (((B, W, ds.total_cells), torch.int16) if targets == "mask"
+                                else ((B, W, ds.total_cells, ds.num_classes), torch.float32))
         self._ring = [(torch.empty((B, W, ds.n_channels, ds.n_mels), dtype=torch.float32, device=dev),
-                       torch.empty((B, W, ds.total_cells, ds.num_classes), dtype=torch.float32, device=dev))
+                       torch.empty(lab_shape, dtype=lab_dtype, device=dev))
                       for _ in range(max(2, int(depth)))]
         self._slot = 0
         self._args = (ds._features_tcf.data_ptr(), ds._features_tcf.shape[0], row)
@@ -492,9 +501,13 @@ class DeviceLoader:
                 break
             spec, lab = self._ring[self._slot]
             self._slot = (self._slot + 1) % len(self._ring)
+            masks = self.targets == "mask"
             check(lib.seld_loader_batch(feat_ptr, rows, row, order_ptr, first, nb, start_ptr, lo_ptr, hi_ptr, W, spec.data_ptr(),
                                         ev_ptr, ce_ptr, ds.I, ds.J, ds.num_classes, 5.0, 5.0,
-                                        lab.data_ptr() if compact else None, stream), "seld_loader_batch")
+                                        lab.data_ptr() if compact and not masks else None, stream), "seld_loader_batch")
+            if masks:
+                check(lib.seld_batch_class_mask(order_ptr, first, nb, start_ptr, lo_ptr, hi_ptr, W, ev_ptr, ce_ptr, ds.I, ds.J,
+                                                ds.num_classes, 5.0, 5.0, lab.data_ptr(), stream), "seld_batch_class_mask")
             if not compact:  # dense labels resident in HBM: gather their windows
                 l = ds.concatenated_labels
                 starts_dev = self._win_start64[order[first:first + nb].long()]

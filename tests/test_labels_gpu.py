@@ -279,3 +279,47 @@ def test_sharded_dataset_windows_equal_the_unsharded_ones(sb, label_mode, gaussi
                 k += 1
     assert seen == list(range(len(full)))
     assert res[0][1] == 0 and res[0][2] > 0 and res[1][2] == 0  # rank 0 reads a halo from rank 1; the last rank pads
+
+
+# ---- N4: class loss from compact targets (reference loss.py:27-54) ----
+@pytest.mark.parametrize("gaussian", [False, True])
+def test_compact_loss_equals_reference_loss_on_dense_labels(sb, gaussian):
+    """softmax-MSE and (weighted) cross entropy, value and gradient, from the int16 class-set masks == the reference's
+    formulas (restated in oracle/ref_port.py) on the dense labels of the same batches — including multi-hot cells, class-13
+    events (weird.csv) and padded tail windows."""
+    from oracle import ref_port
+    files = {"synthetic://a": ("noise", 97440, 31), "synthetic://b": ("noise", 48480, 32), "synthetic://c": ("noise", 60000, 33)}
+    csvs = [cases.csv_path("edges"), cases.csv_path("weird"), cases.csv_path("floatcol")]
+    np.random.seed(3)
+    ds = sb.SELDDataset(list(files), csvs, use_gaussian_augmentation=gaussian, audio_loader=_fake_loader(files), resident="cuda",
+                        labels="compact", feature_type="foa_iv")
+    dense = sb.DeviceLoader(ds, batch_size=4)
+    masks = sb.DeviceLoader(ds, batch_size=4, targets="mask")
+    g = torch.Generator().manual_seed(1)
+    w = (torch.rand(14, generator=g) + 0.5).cuda()
+    for (spec_d, lab), (spec_m, mask) in zip(dense, masks):
+        assert torch.equal(spec_d, spec_m) and mask.dtype == torch.int16 and mask.shape == lab.shape[:3]
+        # the mask IS the dense label: bit c <=> lab[..., c] == 1, 0 <=> one-hot background
+        bits = (lab[..., :] != 0).to(torch.int32) * (1 << torch.arange(14, device="cuda", dtype=torch.int32))
+        want_mask = bits.sum(-1)
+        want_mask = torch.where(want_mask == (1 << 13), torch.zeros_like(want_mask), want_mask)
+        got_mask = mask.to(torch.int32) & 0xffff
+        only_bg_event = (got_mask == (1 << 13))  # a class-13 event alone: mask bit 13 set, dense row identical to background
+        assert torch.equal(torch.where(only_bg_event, torch.zeros_like(got_mask), got_mask), want_mask)
+        z = (3.0 * torch.randn(lab.shape, generator=g)).cuda()
+        for loss_type, weights in (("mse", None), ("ce", None), ("ce", w)):
+            z1 = z.clone().requires_grad_(True)
+            ref = (ref_port.class_mse_loss_port(z1, lab) if loss_type == "mse" else ref_port.class_ce_loss_port(z1, lab, weights))
+            (2.5 * ref).backward()
+            # the same formulas in float64: torch's float32 mean over 2.6 M cells is itself only good to ~1e-5 relative,
+            # the kernel accumulates in float64
+            ref64 = (ref_port.class_mse_loss_port(z.double(), lab.double()) if loss_type == "mse"
+                     else ref_port.class_ce_loss_port(z.double(), lab.double(), None if weights is None else weights.double()))
+            z2 = z.clone().requires_grad_(True)
+            crit = sb.CompactSMRSELDLoss(loss_type=loss_type, w_class=2.5, grid_size=(18, 36), class_weights=weights)
+            total, breakdown = crit(z2, mask)
+            total.backward()
+            assert abs(breakdown[f"class_{loss_type}"] - float(ref64)) <= 2e-6 * max(1.0, abs(float(ref64)))
+            assert abs(breakdown[f"class_{loss_type}"] - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
+            assert torch.allclose(total.double(), 2.5 * ref64, rtol=2e-6, atol=1e-9)
+            assert torch.allclose(z2.grad, z1.grad, rtol=1e-4, atol=1e-12 + 1e-5 * float(z1.grad.abs().max()))
