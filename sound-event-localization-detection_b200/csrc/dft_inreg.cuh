@@ -96,10 +96,44 @@ SELD_HD float2 cscale(float2 a, float w) {
     return make_float2(a.x * w, a.y * w);
 #endif
 }
-SELD_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
-SELD_HD float2 cmul_conj(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
+// Complex multiply a * w.  On sm_100a: TWO packed instructions (FMUL2 + FFMA2) instead of two FMUL + two FFMA — the
+// twiddle is one 64-bit operand (.F32x2.HI_LO, and swapped / half-negated .LO_HI.NP for the second product), a.x and a.y
+// are scalar-broadcast operands (.F32).  Same roundings as the scalar form.
+SELD_HD float2 cmul(float2 a, float2 w) {
+#ifdef __CUDA_ARCH__
+    float2 r;
+    asm("{.reg .b64 rw, rws, ra, rb, t; mov.b64 rw, {%4, %5}; mov.b64 rws, {%6, %4}; mov.b64 ra, {%2, %2}; mov.b64 rb, {%3, %3};"
+        " mul.rn.f32x2 t, rw, ra; fma.rn.f32x2 t, rws, rb, t; mov.b64 {%0, %1}, t;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(w.x), "f"(w.y), "f"(-w.y));
+    return r;
+#else
+    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+#endif
+}
+SELD_HD float2 cmul_conj(float2 a, float2 w) { return cmul(a, make_float2(w.x, -w.y)); }
 SELD_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 SELD_HD float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
+
+// Compile-time twiddles live in constant memory as (c, s, -s, c): ptxas loads them into UNIFORM registers outside the
+// frame loop (LDCU) and the packed multiply takes them as 64-bit uniform operands, so a * W_N^K is the same two packed
+// instructions with no vector register spent on the constant.
+struct TwQuad { float c, s, ns, c2; };
+template <int N>
+struct TwTable { TwQuad q[N]; };
+template <int N>
+constexpr TwTable<N> make_tw_table(bool inv) {
+    TwTable<N> t{};
+    for (int k = 0; k < N; ++k) {
+        const float c = float(cx_cos2pi(k, N));
+        const float s = float(inv ? cx_sin2pi(k, N) : -cx_sin2pi(k, N));
+        t.q[k] = TwQuad{c, s, -s, c};
+    }
+    return t;
+}
+#ifdef __CUDACC__
+template <int N, bool INV>
+__constant__ TwTable<N> kTwConst = make_tw_table<N>(INV);
+#endif
 
 // a * W_N^K (forward) or a * conj(W_N^K) (INV), K and N compile-time.
 template <int K, int N, bool INV = false>
@@ -114,9 +148,18 @@ SELD_HD float2 mul_w(float2 a) {
     } else if constexpr (4 * k == 3 * N) {
         return INV ? mul_mi(a) : mul_pi(a);
     } else {
+#ifdef __CUDA_ARCH__
+        const TwQuad& q = kTwConst<N, INV>.q[k];
+        float2 r;
+        asm("{.reg .b64 rw, rws, ra, rb, t; mov.b64 rw, {%4, %5}; mov.b64 rws, {%6, %7}; mov.b64 ra, {%2, %2}; mov.b64 rb, {%3, %3};"
+            " mul.rn.f32x2 t, rw, ra; fma.rn.f32x2 t, rws, rb, t; mov.b64 {%0, %1}, t;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(q.c), "f"(q.s), "f"(q.ns), "f"(q.c2));
+        return r;
+#else
         constexpr float c = float(cx_cos2pi(k, N));
         constexpr float s = float(INV ? cx_sin2pi(k, N) : -cx_sin2pi(k, N));
         return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+#endif
     }
 }
 

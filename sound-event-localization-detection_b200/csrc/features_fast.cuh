@@ -91,6 +91,17 @@ __device__ __forceinline__ float2 pow_pair(float2 s, float2 d) {
     return r;
 }
 
+// t = m0 * (m1a, m1b);  result = f0 * (f1a, f1b) + t: two packed instructions.  ptxas folds a swap and a negated half of
+// the pair (f1a, f1b) into the FFMA2 operand (.LO_HI / .NP), so sums of two products like Re(conj(a) b) pairs cost 2
+// instructions instead of 4.
+__device__ __forceinline__ float2 mul_fma_pair(float m0, float m1a, float m1b, float f0, float f1a, float f1b) {
+    float2 r;
+    asm("{.reg .b64 a, b, c, e, t; mov.b64 a, {%2, %2}; mov.b64 b, {%3, %4}; mov.b64 c, {%5, %5}; mov.b64 e, {%6, %7};"
+        " mul.rn.f32x2 t, a, b; fma.rn.f32x2 t, e, c, t; mov.b64 {%0, %1}, t;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(m0), "f"(m1a), "f"(m1b), "f"(f0), "f"(f1a), "f"(f1b));
+    return r;
+}
+
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ float sample_of(const float* p) { return __ldg(p); }
@@ -514,11 +525,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             if (pr == 0) {
                 // ---- park X0 = (s.x, d.y), P1 = |X1|^2 and I1 = Re(conj(X0) X1) in planes 0..3 (same lane reads them back) ----
                 auto park = [&](int k, float2 sS, float2 dD) {
-                    const float p1 = fmaf(sS.y, sS.y, dD.x * dD.x), i1 = fmaf(sS.x, sS.y, -(dD.x * dD.y));
+                    // (I1, P1) = s.y * (s.x, s.y) + d.x * (-d.y, d.x)   [X0 = (s.x, d.y), X1 = (s.y, -d.x)]
+                    const float2 ip = mul_fma_pair(sS.y, sS.x, sS.y, dD.x, -dD.y, dD.x);
                     region[k] = sS.x;
                     region[L::PITCH + k] = dD.y;
-                    region[2 * L::PITCH + k] = p1;
-                    region[3 * L::PITCH + k] = i1;
+                    region[2 * L::PITCH + k] = ip.y;
+                    region[3 * L::PITCH + k] = ip.x;
                 };
                 static_for<16>([&](auto KH) {
                     float2 sS, dD;
@@ -564,16 +576,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
                     region[2 * L::PITCH + k] = p23.x;
                     region[3 * L::PITCH + k] = p23.y;
                     if (IV) {
-                        const float i2 = fmaf(x0r, sS.x, x0i * dD.y);     // Re(conj(X0) X2), X2 = (s.x, d.y)
-                        const float i3 = fmaf(x0r, sS.y, -(x0i * dD.x));  // Re(conj(X0) X3), X3 = (s.y, -d.x)
+                        // (I2, I3) = (Re(conj(X0) X2), Re(conj(X0) X3)) = x0r * (s.x, s.y) + x0i * (d.y, -d.x)
+                        const float2 i23 = mul_fma_pair(x0r, sS.x, sS.y, x0i, dD.y, -dD.x);
                         float e;
                         if constexpr (BF) e = fmaf(p23.y, k3, fmaf(p23.x, k2, fmaf(p1, k1, fmaf(p0, k0, kEpsIV))));
                         else e = kEpsIV + p0 + (p1 + p23.x + p23.y) * (1.0f / 3.0f);
                         float inv;  // MUFU.RCP alone (1 ulp): e >= 1e-8 is never denormal; the IV tolerance is 1e-4 relative
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(e));
+                        const float2 i23n = cscale(i23, inv);
                         region[4 * L::PITCH + k] = i1 * inv;
-                        region[5 * L::PITCH + k] = i2 * inv;
-                        region[6 * L::PITCH + k] = i3 * inv;
+                        region[5 * L::PITCH + k] = i23n.x;
+                        region[6 * L::PITCH + k] = i23n.y;
                     }
                 };
                 static_for<16>([&](auto KH) {

@@ -47,13 +47,13 @@ struct MicLayout {
 // x / |x| (0 for an exactly-zero bin: the clamp keeps rsqrt finite and 0 * finite = 0); keep = 0 for a silent channel
 __device__ __forceinline__ float2 mic_unit(float2 x, float p, float keep) {
     const float r = rsqrtf(fmaxf(p, 1e-37f)) * keep;
-    return make_float2(x.x * r, x.y * r);
+    return cscale(x, r);
 }
 // conj(a) * b for unit phasors.  A digitally silent channel has zero phasors, so its pairs give G == 0 here; the
 // definition R == 0 -> exp(j*angle(0)) = 1 (a delta at lag 0) is restored at the store, where it costs one add per pair
 // instead of a test per bin (by linearity: irfft(1) = delta).
-__device__ __forceinline__ float2 mic_phat(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.x, b.y, -(a.y * b.x)));
+__device__ __forceinline__ float2 mic_phat(float2 a, float2 b) {  // a.x * (b.x, b.y) + a.y * (b.y, -b.x): 2 packed instructions
+    return mul_fma_pair(a.x, b.x, b.y, a.y, b.y, -b.x);
 }
 template <int S>
 __device__ __forceinline__ void mic_pick(float4 q, float4 s, float2& ga, float2& gb) {
@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
                     const float4 q = Q[active ? lane + R1 * kh : 0];
                     float2 ga, gb;
                     mic_pick<SS>(q, U23[kh], ga, gb);
-                    float2 g = make_float2(ga.x - gb.y, ga.y + gb.x);     // G_a + i G_b
-                    mir[kh] = make_float2(ga.x + gb.y, gb.x - ga.y);      // conj(G_a) + i conj(G_b) = bin N-k
+                    float2 g = cadd(ga, make_float2(-gb.y, gb.x));                       // G_a + i G_b
+                    mir[kh] = cadd(make_float2(ga.x, -ga.y), make_float2(gb.y, gb.x));   // conj(G_a) + i conj(G_b) = bin N-k
                     if (kh == 0) {  // lane 0 holds DC there: imaginary parts dropped like irfft
                         g.x = lane == 0 ? ga.x : g.x;
                         g.y = lane == 0 ? gb.x : g.y;
