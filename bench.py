@@ -389,12 +389,16 @@ def run_train_step(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ds = _synthetic_dataset(dev, n_files=16, seed=rank)  # every rank owns its shard of clips
-    dl = seld_b200.DeviceLoader(ds, batch_size=16, shuffle=True, drop_last=True, generator=torch.Generator().manual_seed(rank))
+    dl = seld_b200.DeviceLoader(ds, batch_size=16, shuffle=True, drop_last=True, generator=torch.Generator().manual_seed(rank),
+                                targets="mask" if args.compact_loss else "dense")
     torch.manual_seed(0)
     model = SELD_Conformer(n_channels=7, n_mels=N_MELS, grid_size=(ds.I, ds.J), num_classes=14).to(dev)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
-    criterion = SMRSELDLoss(loss_type="mse", grid_size=(ds.I, ds.J))  # config.py:71 LOSS_TYPE = 'mse'
+    if args.compact_loss:  # N4: int16 class-set masks + seld_class_loss instead of dense targets + the reference loss
+        criterion = seld_b200.CompactSMRSELDLoss(loss_type="mse", grid_size=(ds.I, ds.J))
+    else:
+        criterion = SMRSELDLoss(loss_type="mse", grid_size=(ds.I, ds.J))  # config.py:71 LOSS_TYPE = 'mse'
     optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)
     model.train()
 
@@ -447,7 +451,8 @@ def run_train_step(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[4]: on-device front-end (features + Gaussian label targets per batch of 16 windows x "
                                "250 frames) feeding the reference SELD_Conformer(n_channels=7) train step, 16 x 60 s clips per GPU",
-                   "model": "reference model_conformer.SELD_Conformer + loss.SMRSELDLoss('mse') + Adam (staged in baseline/_ref, fp32)",
+                   "model": ("reference model_conformer.SELD_Conformer + " + ("seld_b200.CompactSMRSELDLoss('mse') on int16 class-set masks (N4)"
+                             if args.compact_loss else "loss.SMRSELDLoss('mse')") + " + Adam (staged in baseline/_ref, fp32)"),
                    "parallelism": f"ddp{world}" if world > 1 else "single GPU", "timing": "wall clock; per-part CUDA events"},
         "frontend_ms_per_step": fe, "model_ms_per_step": md, "frontend_fraction_of_step": fe / (fe + md),
         "reference_frontend_bytes_h2d_per_step": 16 * 250 * (7 * 64 + 648 * 14) * 4, "last_loss": lv,
@@ -513,6 +518,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--compact-loss", action="store_true", help="--workload train_step: class-set masks + seld_class_loss (N4)")
     ap.add_argument("--corpus-clips", type=int, default=600, help="--workload corpus: clips of the whole job (~10 h at 600)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

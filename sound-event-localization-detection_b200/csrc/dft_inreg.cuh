@@ -99,8 +99,10 @@ SELD_HD float2 cscale(float2 a, float w) {
 // Complex multiply a * w.  On sm_100a: TWO packed instructions (FMUL2 + FFMA2) instead of two FMUL + two FFMA — the
 // twiddle is one 64-bit operand (.F32x2.HI_LO, and swapped / half-negated .LO_HI.NP for the second product), a.x and a.y
 // are scalar-broadcast operands (.F32).  Same roundings as the scalar form.
+// (SELD_SCALAR_CMUL, defined by a translation unit before this header, keeps the four-instruction scalar form: the MIC
+//  kernel is FP32-pipe-bound rather than issue-bound and measured 7 % slower with the packed form.)
 SELD_HD float2 cmul(float2 a, float2 w) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(SELD_SCALAR_CMUL)
     float2 r;
     asm("{.reg .b64 rw, rws, ra, rb, t; mov.b64 rw, {%4, %5}; mov.b64 rws, {%6, %4}; mov.b64 ra, {%2, %2}; mov.b64 rb, {%3, %3};"
         " mul.rn.f32x2 t, rw, ra; fma.rn.f32x2 t, rws, rb, t; mov.b64 {%0, %1}, t;}"
@@ -148,7 +150,7 @@ SELD_HD float2 mul_w(float2 a) {
     } else if constexpr (4 * k == 3 * N) {
         return INV ? mul_mi(a) : mul_pi(a);
     } else {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(SELD_SCALAR_CMUL)
         const TwQuad& q = kTwConst<N, INV>.q[k];
         float2 r;
         asm("{.reg .b64 rw, rws, ra, rb, t; mov.b64 rw, {%4, %5}; mov.b64 rws, {%6, %7}; mov.b64 ra, {%2, %2}; mov.b64 rb, {%3, %3};"

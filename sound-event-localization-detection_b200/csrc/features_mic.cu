@@ -21,6 +21,9 @@
 // |windowed sample| per channel, FMNMX3 + CREDUX); phases do not see the factor, the mel rows are un-scaled by it.
 // n_fft 1024 (R1 = 32) and 960 (R1 = 30, the reference's default config.py:85): for 960 the inverse runs over 30 lanes
 // with its own twiddle table W_960^(k_lo t_lo).
+// This kernel is bound by the FP32 pipe rather than by issue slots: the packed two-instruction complex multiply of
+// dft_inreg.cuh measured 3-7 % SLOWER here than the four scalar instructions (tools/mic_ab.sh), so it keeps the scalar form.
+#define SELD_SCALAR_CMUL
 #include "features_fast.cuh"
 
 namespace seld {
@@ -47,13 +50,13 @@ struct MicLayout {
 // x / |x| (0 for an exactly-zero bin: the clamp keeps rsqrt finite and 0 * finite = 0); keep = 0 for a silent channel
 __device__ __forceinline__ float2 mic_unit(float2 x, float p, float keep) {
     const float r = rsqrtf(fmaxf(p, 1e-37f)) * keep;
-    return cscale(x, r);
+    return make_float2(x.x * r, x.y * r);
 }
 // conj(a) * b for unit phasors.  A digitally silent channel has zero phasors, so its pairs give G == 0 here; the
 // definition R == 0 -> exp(j*angle(0)) = 1 (a delta at lag 0) is restored at the store, where it costs one add per pair
 // instead of a test per bin (by linearity: irfft(1) = delta).
-__device__ __forceinline__ float2 mic_phat(float2 a, float2 b) {  // a.x * (b.x, b.y) + a.y * (b.y, -b.x): 2 packed instructions
-    return mul_fma_pair(a.x, b.x, b.y, a.y, b.y, -b.x);
+__device__ __forceinline__ float2 mic_phat(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 template <int S>
 __device__ __forceinline__ void mic_pick(float4 q, float4 s, float2& ga, float2& gb) {
@@ -305,8 +308,8 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
                     const float4 q = Q[active ? lane + R1 * kh : 0];
                     float2 ga, gb;
                     mic_pick<SS>(q, U23[kh], ga, gb);
-                    float2 g = cadd(ga, make_float2(-gb.y, gb.x));                       // G_a + i G_b
-                    mir[kh] = cadd(make_float2(ga.x, -ga.y), make_float2(gb.y, gb.x));   // conj(G_a) + i conj(G_b) = bin N-k
+                    float2 g = make_float2(ga.x - gb.y, ga.y + gb.x);     // G_a + i G_b
+                    mir[kh] = make_float2(ga.x + gb.y, gb.x - ga.y);      // conj(G_a) + i conj(G_b) = bin N-k
                     if (kh == 0) {  // lane 0 holds DC there: imaginary parts dropped like irfft
                         g.x = lane == 0 ? ga.x : g.x;
                         g.y = lane == 0 ? gb.x : g.y;

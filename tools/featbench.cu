@@ -132,7 +132,8 @@ int main(int argc, char** argv) {
         Lib* lp = &L[i];
         auto add = [&](const char* nm, int mode, int c_out, double* st) {
             cases.push_back({l.name + ": " + nm, bytes_of(c_out, 4, 4), [=] {
-                if (lp->features(lp->plan, mode, audio, C * N, N, N, nullptr, B, C, out, T, c_out, 0, st, nullptr, nullptr, nullptr) != 0) { printf("features: %s\n", lp->last_error()); exit(1); }
+                const int rc = lp->features(lp->plan, mode, audio, C * N, N, N, nullptr, B, C, out, T, c_out, 0, st, nullptr, nullptr, nullptr);
+                if (rc != 0) { printf("features (%s, mode %d): rc %d: %s | %s\n", lp->name.c_str(), mode, rc, lp->last_error(), cudaGetErrorString(cudaGetLastError())); exit(1); }
             }, {}});
         };
         add("foa (7 ch)", 1, 7, nullptr);
