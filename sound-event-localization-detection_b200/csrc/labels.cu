@@ -52,6 +52,30 @@ __device__ __forceinline__ bool cell_in_region(int gi, int gj, int I, int J, dou
     return (fabs(diff) <= two_s_az) && (el_min <= cell_el) && (cell_el <= el_max);
 }
 
+// Candidate cells of a region event: a box of grid cells that contains every cell the exact test can accept (its
+// half-width is 2 sigma plus one cell of margin in each direction; azimuth wraps, elevation clamps).  The exact float64
+// test still decides each candidate, so the result is that of testing all I*J cells (smrl_seld_gaussian.py:485-518) —
+// 9-25 evaluations instead of 648.
+struct RegionBox { int i0, ni, j0, nj; };
+__device__ __forceinline__ RegionBox region_box(int I, int J, double c_az, double c_el, double two_s_az, double two_s_el) {
+    const double ch = 180.0 / (double)I, cw = 360.0 / (double)J;
+    RegionBox b;
+    int ri = (int)ceil(two_s_el / ch) + 1, rj = (int)ceil(two_s_az / cw) + 1;
+    int ic = (int)floor((c_el + 90.0) / ch), jc = (int)floor((c_az + 180.0) / cw);
+    if (!(two_s_el >= 0.0) || !(two_s_az >= 0.0) || !(fabs(c_el) < 1e6) || !(fabs(c_az) < 1e6) || ri > I || rj > J) {
+        b.i0 = 0; b.ni = I; b.j0 = 0; b.nj = J;  // degenerate inputs: test every cell, like the reference
+        return b;
+    }
+    int i0 = ic - ri, i1 = ic + ri;
+    i0 = i0 < 0 ? 0 : i0;
+    i1 = i1 > I - 1 ? I - 1 : i1;
+    b.i0 = i0;
+    b.ni = i1 >= i0 ? i1 - i0 + 1 : 0;
+    if (2 * rj + 1 >= J) { b.j0 = 0; b.nj = J; }
+    else { b.j0 = ((jc - rj) % J + J) % J; b.nj = 2 * rj + 1; }
+    return b;
+}
+
 // one CTA per event; pass 0: background <- 0, pass 1: class <- 1
 __global__ void labels_paint_kernel(float* __restrict__ out, long long rows, int I, int J, int M,
                                     const int4* __restrict__ events, const double2* __restrict__ centres,
@@ -71,8 +95,11 @@ __global__ void labels_paint_kernel(float* __restrict__ out, long long rows, int
         return;
     }
     const double2 c = centres[blockIdx.x];
-    for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
-        if (!cell_in_region(cell / J, cell % J, I, J, c.x, c.y, two_s_az, two_s_el)) continue;
+    const RegionBox bx = region_box(I, J, c.x, c.y, two_s_az, two_s_el);
+    for (int q = threadIdx.x; q < bx.ni * bx.nj; q += blockDim.x) {
+        const int gi = bx.i0 + q / bx.nj, gj = (bx.j0 + q % bx.nj) % J;
+        if (!cell_in_region(gi, gj, I, J, c.x, c.y, two_s_az, two_s_el)) continue;
+        const int cell = gi * J + gj;
         for (long long r = row0; r < row1; ++r) out[(r * cells + cell) * M + col] = val;
     }
 }
@@ -314,8 +341,11 @@ __global__ void __launch_bounds__(256) loader_batch_kernel(
                         lab[((r - g0) * cells + ev.w) * M + col] = val;
                 } else if (centres) {
                     const double2 c = centres[e2];
-                    for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
-                        if (!cell_in_region(cell / J, cell % J, I, J, c.x, c.y, two_s_az, two_s_el)) continue;
+                    const RegionBox bx = region_box(I, J, c.x, c.y, two_s_az, two_s_el);
+                    for (int q = threadIdx.x; q < bx.ni * bx.nj; q += blockDim.x) {
+                        const int gi = bx.i0 + q / bx.nj, gj = (bx.j0 + q % bx.nj) % J;
+                        if (!cell_in_region(gi, gj, I, J, c.x, c.y, two_s_az, two_s_el)) continue;
+                        const int cell = gi * J + gj;
                         for (long long r = r0; r < r1; ++r) lab[((r - g0) * cells + cell) * M + col] = val;
                     }
                 }

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) batch_class_mask_kernel(const int* __rest
             auto or_at = [&](long long idx) { atomicOr(m32 + (idx >> 1), (idx & 1) ? bit << 16 : bit); };
             if (ev.w >= 0) {
                 for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x) or_at((r - g0) * cells + ev.w);
-            } else if (centres) {
+            } else if (centres) {  // (all cells are tested here: the mask path is 3 % of a batch, see labels.cu for the boxed form)
                 const double2 c = centres[e2];
                 for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
                     if (!loss_cell_in_region(cell / J, cell % J, I, J, c.x, c.y, two_s_az, two_s_el)) continue;

@@ -323,3 +323,34 @@ def test_compact_loss_equals_reference_loss_on_dense_labels(sb, gaussian):
             assert abs(breakdown[f"class_{loss_type}"] - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
             assert torch.allclose(total.double(), 2.5 * ref64, rtol=2e-6, atol=1e-9)
             assert torch.allclose(z2.grad, z1.grad, rtol=1e-4, atol=1e-12 + 1e-5 * float(z1.grad.abs().max()))
+
+
+def test_region_candidate_box_equals_exhaustive_test(sb):
+    """The paint kernels evaluate the exact float64 region test only on a box of candidate cells around the centre.  Against
+    the oracle's exhaustive loop over all I*J cells: centres on cell-centre boundaries (the <= comparisons decide), at the
+    azimuth wrap, beyond the poles, out of range, with sigmas from 0 to larger than the sphere, on four grids."""
+    rng = np.random.default_rng(42)
+    lib, check = sb._lib.lib(), sb._lib.check
+    stream = torch.cuda.current_stream().cuda_stream
+    for (I, J) in ((18, 36), (9, 18), (36, 72), (12, 24)):
+        centres, sig = [], []
+        special = [-185.0, -180.0, -175.0, -5.0, 0.0, 5.0, 175.0, 180.0, 185.0, 355.0, -400.0, 720.0]
+        for az in special:
+            for el in (-95.0, -90.0, -85.0, -5.0, 0.0, 85.0, 90.0, 100.0, 200.0):
+                centres.append((az, el))
+        for _ in range(150):
+            centres.append((float(rng.uniform(-400, 400)), float(rng.uniform(-200, 200))))
+        for sa, se in ((5.0, 5.0), (0.0, 0.0), (2.5, 2.5), (2.4999, 7.5), (12.5, 3.0), (45.0, 45.0), (95.0, 50.0), (0.01, 30.0)):
+            ev = np.array([[k, k + 1, k % 13, -1] for k in range(len(centres))], dtype=np.int32)
+            ce = np.array(centres, dtype=np.float64)
+            out = torch.empty((len(centres), I * J, 14), dtype=torch.float32, device="cuda")
+            check(lib.seld_labels_fill(out.data_ptr(), out.shape[0], I * J, 14, stream), "fill")
+            ev_d, ce_d = torch.from_numpy(ev).cuda(), torch.from_numpy(ce).cuda()
+            check(lib.seld_labels_paint(out.data_ptr(), out.shape[0], I, J, 14, ev_d.data_ptr(), ce_d.data_ptr(), len(ev), sa, se,
+                                        stream), "paint")
+            got = out.cpu().numpy()
+            for k, (az, el) in enumerate(centres):
+                want = np.zeros(I * J, bool)
+                want[ol.region_cells(az, el, sa, se, I, J)] = True
+                assert np.array_equal(got[k, :, k % 13] == 1.0, want), (I, J, az, el, sa, se)
+                assert np.array_equal(got[k, :, 13] == 0.0, want)
