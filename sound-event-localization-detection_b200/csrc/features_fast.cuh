@@ -45,7 +45,13 @@
 
 #include "mel_baked.h"
 #include "seld_common.h"
+#include "tmem_store.cuh"
 #include "warp_fft.cuh"
+
+// 1: the per-lane constant rows (window, pass-1 twiddles) live in tensor memory instead of shared memory (tmem_store.cuh)
+#ifndef SELD_TMEM
+#define SELD_TMEM 1
+#endif
 
 namespace seld {
 
@@ -53,6 +59,8 @@ constexpr int kBfMinShift = 3;    // BF kernel: exponent difference below which 
 constexpr int kBfMaxShift = 60;   // largest applied shift: 2^-120 for the powers stays a normal float
 constexpr int kRedoLog2 = 12;     // LEAN kernel: pair power ratio (log2) above which a frame goes to the redo list
 constexpr int kRedoCap = 1 << 16; // redo list capacity (frames); beyond it the BF kernel redoes the whole call
+constexpr bool kTm = SELD_TMEM != 0;
+constexpr int kTmWinCol = 0, kTmTwCol = 32;  // TMEM columns: window row [32], twiddle row [32 x (re, im)]
 
 template <int R1>
 struct FastLayout {
@@ -208,6 +216,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
     constexpr int N = F::N, NB = F::NB;
     constexpr int NCH = IV ? 7 : 4, NF = NCH * 64;
     constexpr int G = WARPS / 4;
+    // tensor-memory loads of the float32 kernel are issued ahead of the code that hides them and completed later (-1.5 %
+    // against issue + wait in one place); with the int16 / run-time-option epilogues that form measured 0.3-1.8 % slower
+    constexpr bool kTmAsync = EPI == 0 && !IN16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     // work items (frames) are 32-bit: the ABI rejects B * T_out >= 2^31
@@ -223,18 +234,58 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
         }  // else: the list overflowed, redo every frame of the call
     }
 
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     float* s_win = reinterpret_cast<float*>(smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * L::WIN_PITCH);
-    float* s_regions = reinterpret_cast<float*>(s_tw + 32 * L::TW_PITCH);
+    float* s_regions = kTm ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(s_tw + 32 * L::TW_PITCH);
     float* s_norm = s_regions + WARPS * L::REGION;                 // EPI == 2: [2][NF] mean, 1/std
+    uint32_t tm_base = 0, tm_lane = 0;
 
-    for (int i = threadIdx.x; i < 32 * L::WIN_PITCH; i += blockDim.x) {
-        const int l = i / L::WIN_PITCH, j = i - l * L::WIN_PITCH;
-        s_win[i] = j < R1 ? p.window[l + 32 * j] * (IN16 ? (1.0f / 32768.0f) : 1.0f) : 0.f;
-    }
-    for (int i = threadIdx.x; i < 32 * L::TW_PITCH; i += blockDim.x) {
-        const int l = i / L::TW_PITCH, k = i - l * L::TW_PITCH;
-        s_tw[i] = k < R1 ? p.twiddle[k * 32 + l] : make_float2(0.f, 0.f);
+    if constexpr (kTm) {
+        // constant rows of a lane -> tensor memory: thread i of a warp owns TMEM lane 32 (warp % 4) + i, so warps 0..3
+        // fill the four lane quarters and every warp reads the quarter of its own position
+        __shared__ uint32_t s_tm_slot;
+        if (warp == 0) tmem::alloc_all(&s_tm_slot);
+        tmem::fence_before_sync();
+        __syncthreads();
+        tmem::fence_after_sync();
+        tm_base = s_tm_slot;
+        tm_lane = tmem::lane_base(tm_base, warp);
+        if (warp < 4) {
+            float r[16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = 16 * c + i;
+                    r[i] = j < R1 ? p.window[lane + 32 * j] * (IN16 ? (1.0f / 32768.0f) : 1.0f) : 0.f;
+                }
+                tmem::st16(tm_lane + kTmWinCol + 16 * c, r);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 8 * c + i;
+                    const float2 t = k < R1 ? p.twiddle[k * 32 + lane] : make_float2(0.f, 0.f);
+                    r[2 * i] = t.x;
+                    r[2 * i + 1] = t.y;
+                }
+                tmem::st16(tm_lane + kTmTwCol + 16 * c, r);
+            }
+            tmem::wait_st();
+        }
+        tmem::fence_before_sync();
+    } else {
+        for (int i = threadIdx.x; i < 32 * L::WIN_PITCH; i += blockDim.x) {
+            const int l = i / L::WIN_PITCH, j = i - l * L::WIN_PITCH;
+            s_win[i] = j < R1 ? p.window[l + 32 * j] * (IN16 ? (1.0f / 32768.0f) : 1.0f) : 0.f;
+        }
+        for (int i = threadIdx.x; i < 32 * L::TW_PITCH; i += blockDim.x) {
+            const int l = i / L::TW_PITCH, k = i - l * L::TW_PITCH;
+            s_tw[i] = k < R1 ? p.twiddle[k * 32 + l] : make_float2(0.f, 0.f);
+        }
     }
     if constexpr (EPI == 2)
         for (int i = threadIdx.x; i < NF; i += blockDim.x) {
@@ -242,9 +293,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             s_norm[NF + i] = a.inv_std ? a.inv_std[a.c_off * 64 + i] : 1.f;
         }
     __syncthreads();
+    if constexpr (kTm) tmem::fence_after_sync();
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int group = warp >> 2, wi = warp & 3;
     float* region = s_regions + warp * L::REGION;
     float* gregion = s_regions + (group * 4) * L::REGION;
@@ -384,11 +434,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
         for (int pr = 0; pr < 2; ++pr) {
             // ---- window + pass 1 + twiddle (registers only) ----
             // this lane's window row (a constant table: fetched before the barrier so that the loads are in flight)
-            float4 wreg[(R1 + 3) / 4];
-            {
+            float wv[32];
+            if constexpr (kTm) {
+                if constexpr (kTmAsync) tmem::ld32_issue(tm_lane + kTmWinCol, wv);
+            } else {
                 const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * L::WIN_PITCH);
 #pragma unroll
-                for (int i = 0; i < (R1 + 3) / 4; ++i) wreg[i] = wrow[i];
+                for (int i = 0; i < (R1 + 3) / 4; ++i) {
+                    const float4 w4 = wrow[i];
+                    wv[4 * i] = w4.x, wv[4 * i + 1] = w4.y, wv[4 * i + 2] = w4.z, wv[4 * i + 3] = w4.w;
+                }
             }
             // the other warps of the group have finished reading this region (previous mel phase); the previous
             // frame's row is complete (all four filter chunks staged): its copy-out overlaps the first pass below
@@ -414,17 +469,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
                 }
             }
             // window (pre-scaled by 1/2; by 1/65536 for int16 input)
-            static_for<(R1 + 3) / 4>([&](auto Jq) {
-                constexpr int j0 = 4 * decltype(Jq)::value;
-                const float4 w4 = wreg[j0 / 4];
-                static_for<4>([&](auto Ji) {
-                    constexpr int j = j0 + decltype(Ji)::value;
-                    if constexpr (j < R1) {
-                        const float w = decltype(Ji)::value == 0 ? w4.x : decltype(Ji)::value == 1 ? w4.y : decltype(Ji)::value == 2 ? w4.z : w4.w;
-                        v[j] = cscale(v[j], w);
-                    }
-                });
-            });
+            if constexpr (kTm) {
+                if constexpr (kTmAsync) tmem::ld32_wait(wv);
+                else tmem::ld32(tm_lane + kTmWinCol, wv);
+            }
+#pragma unroll
+            for (int j = 0; j < R1; ++j) v[j] = cscale(v[j], wv[j]);
             float inv_a = 1.f, inv_b = 1.f;  // BF: 1 / factor applied to channel a, b
             if constexpr (BF) {
                 // Level of the two channels in this frame: max |windowed sample| over the warp (what enters the FFT).
@@ -459,8 +509,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             }
             float2 u[32];
             if constexpr (STRIP < 5) {
-                Dft<R1, false>::run(v);
-                {
+                if constexpr (kTm) {
+                    float tw0[32], tw1[32];  // issued ahead of the in-register DFT, which hides the access
+                    if constexpr (kTmAsync) {
+                        tmem::ld32_issue(tm_lane + kTmTwCol, tw0);
+                        tmem::ld32_issue(tm_lane + kTmTwCol + 32, tw1);
+                        Dft<R1, false>::run(v);
+                        tmem::ld32_wait(tw0);
+                        tmem::ld32_wait(tw1);
+                    } else {
+                        Dft<R1, false>::run(v);
+                        tmem::ld32(tm_lane + kTmTwCol, tw0);
+                        tmem::ld32(tm_lane + kTmTwCol + 32, tw1);
+                    }
+                    static_for<R1>([&](auto Kc) {
+                        constexpr int k = decltype(Kc)::value;
+                        if constexpr (k >= 1 && k < 16) v[k] = cmul(v[k], make_float2(tw0[2 * k], tw0[2 * k + 1]));
+                        if constexpr (k >= 16) v[k] = cmul(v[k], make_float2(tw1[2 * (k - 16)], tw1[2 * (k - 16) + 1]));
+                    });
+                } else {
+                    Dft<R1, false>::run(v);
                     const float4* trow = reinterpret_cast<const float4*>(s_tw + lane * L::TW_PITCH);
                     static_for<(R1 + 1) / 2>([&](auto Kq) {
                         constexpr int k0 = 2 * decltype(Kq)::value;
@@ -676,12 +744,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             }
         }
     }
+    if constexpr (kTm) {
+        tmem::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem::dealloc_all(tm_base);
+    }
 }
 
 template <int R1, int EPI, int WARPS, bool IV>
 constexpr size_t fast_smem_bytes() {
     using L = FastLayout<R1>;
-    return sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH) +
+    return (kTm ? 0 : sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH)) +
            sizeof(float) * ((size_t)WARPS * L::REGION + (EPI == 2 ? 2 * (IV ? 7 : 4) * 64 : 0));
 }
 

@@ -18,6 +18,10 @@
 #include <string>
 #include <vector>
 
+// The kernels compiled HERE live in their own namespace: a kernel instantiated both in this binary and in a dlopen-ed
+// library under the same mangled name was seen to run ONE of the copies for all of them (equal times for builds that
+// differ), so nothing in this binary may share a kernel name with the libraries under test.
+#define seld seld_fb
 #include "../include/seld_cuda.h"
 #include "../sound-event-localization-detection_b200/csrc/features_fast.cuh"
 
