@@ -60,7 +60,7 @@ constexpr int kBfMaxShift = 60;   // largest applied shift: 2^-120 for the power
 constexpr int kRedoLog2 = 12;     // LEAN kernel: pair power ratio (log2) above which a frame goes to the redo list
 constexpr int kRedoCap = 1 << 16; // redo list capacity (frames); beyond it the BF kernel redoes the whole call
 constexpr bool kTm = SELD_TMEM != 0;
-constexpr int kTmWinCol = 0, kTmTwCol = 32;  // TMEM columns: window row [32], twiddle row [32 x (re, im)]
+constexpr int kTmWinCol = 0, kTmTwCol = 32, kTmCols = 128;  // TMEM columns: window row [32], twiddle row [32 x (re, im)]
 
 template <int R1>
 struct FastLayout {
@@ -216,6 +216,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
     constexpr int N = F::N, NB = F::NB;
     constexpr int NCH = IV ? 7 : 4, NF = NCH * 64;
     constexpr int G = WARPS / 4;
+    // the block-floating kernel keeps its tables in shared memory: it has no registers to spare for the tensor-memory
+    // addresses (88 bytes of spills in the frame loop made it 12 % slower), and it only runs over the redo list
+    constexpr bool TM = kTm && !BF;
     // tensor-memory loads of the float32 kernel are issued ahead of the code that hides them and completed later (-1.5 %
     // against issue + wait in one place); with the int16 / run-time-option epilogues that form measured 0.3-1.8 % slower
     constexpr bool kTmAsync = EPI == 0 && !IN16;
@@ -238,15 +241,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
     const int warp = threadIdx.x >> 5;
     float* s_win = reinterpret_cast<float*>(smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * L::WIN_PITCH);
-    float* s_regions = kTm ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(s_tw + 32 * L::TW_PITCH);
+    float* s_regions = TM ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(s_tw + 32 * L::TW_PITCH);
     float* s_norm = s_regions + WARPS * L::REGION;                 // EPI == 2: [2][NF] mean, 1/std
     uint32_t tm_base = 0, tm_lane = 0;
 
-    if constexpr (kTm) {
+    if constexpr (TM) {
         // constant rows of a lane -> tensor memory: thread i of a warp owns TMEM lane 32 (warp % 4) + i, so warps 0..3
         // fill the four lane quarters and every warp reads the quarter of its own position
         __shared__ uint32_t s_tm_slot;
-        if (warp == 0) tmem::alloc_all(&s_tm_slot);
+        if (warp == 0) tmem::alloc<kTmCols>(&s_tm_slot);
         tmem::fence_before_sync();
         __syncthreads();
         tmem::fence_after_sync();
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             s_norm[NF + i] = a.inv_std ? a.inv_std[a.c_off * 64 + i] : 1.f;
         }
     __syncthreads();
-    if constexpr (kTm) tmem::fence_after_sync();
+    if constexpr (TM) tmem::fence_after_sync();
 
     const int group = warp >> 2, wi = warp & 3;
     float* region = s_regions + warp * L::REGION;
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             // ---- window + pass 1 + twiddle (registers only) ----
             // this lane's window row (a constant table: fetched before the barrier so that the loads are in flight)
             float wv[32];
-            if constexpr (kTm) {
+            if constexpr (TM) {
                 if constexpr (kTmAsync) tmem::ld32_issue(tm_lane + kTmWinCol, wv);
             } else {
                 const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * L::WIN_PITCH);
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
                 }
             }
             // window (pre-scaled by 1/2; by 1/65536 for int16 input)
-            if constexpr (kTm) {
+            if constexpr (TM) {
                 if constexpr (kTmAsync) tmem::ld32_wait(wv);
                 else tmem::ld32(tm_lane + kTmWinCol, wv);
             }
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             }
             float2 u[32];
             if constexpr (STRIP < 5) {
-                if constexpr (kTm) {
+                if constexpr (TM) {
                     float tw0[32], tw1[32];  // issued ahead of the in-register DFT, which hides the access
                     if constexpr (kTmAsync) {
                         tmem::ld32_issue(tm_lane + kTmTwCol, tw0);
@@ -744,17 +747,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_fast_kernel(PlanDev p,
             }
         }
     }
-    if constexpr (kTm) {
+    if constexpr (TM) {
         tmem::fence_before_sync();
         __syncthreads();
-        if (warp == 0) tmem::dealloc_all(tm_base);
+        if (warp == 0) tmem::dealloc<kTmCols>(tm_base);
     }
 }
 
-template <int R1, int EPI, int WARPS, bool IV>
+template <int R1, int EPI, int WARPS, bool IV, bool BF>
 constexpr size_t fast_smem_bytes() {
     using L = FastLayout<R1>;
-    return (kTm ? 0 : sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH)) +
+    return (kTm && !BF ? 0 : sizeof(float) * (32 * L::WIN_PITCH) + sizeof(float2) * (32 * L::TW_PITCH)) +
            sizeof(float) * ((size_t)WARPS * L::REGION + (EPI == 2 ? 2 * (IV ? 7 : 4) * 64 : 0));
 }
 
@@ -763,20 +766,20 @@ template <int R1, bool IV, bool IN16, int EPI, int WARPS, bool BF, int STRIP = 0
 static int fast_configure() {
     auto kern = features_fast_kernel<R1, IV, IN16, EPI, WARPS, BF, STRIP>;
     SELD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)fast_smem_bytes<R1, EPI, WARPS, IV>()));
+                                       (int)fast_smem_bytes<R1, EPI, WARPS, IV, BF>()));
     return SELD_OK;
 }
 
 // a.redo_mode (BF kernel only): persistent grid over the redo list, one CTA per SM
 template <int R1, bool IV, bool IN16, int EPI, int WARPS, bool BF, int STRIP = 0>
 static int fast_launch(const seld_plan* plan, const FeatArgs& a, cudaStream_t stream) {
-    static_assert(fast_smem_bytes<R1, EPI, WARPS, IV>() <= (size_t)kMaxSmemOptin, "shared memory budget (227 KB)");
+    static_assert(fast_smem_bytes<R1, EPI, WARPS, IV, BF>() <= (size_t)kMaxSmemOptin, "shared memory budget (227 KB)");
     const long long n_gitems = (a.n_items + 3) / 4;
     long long ctas = (n_gitems + WARPS / 4 - 1) / (WARPS / 4);
     if (ctas > plan->num_sms) ctas = plan->num_sms;
     if (ctas < 1) return SELD_OK;
     features_fast_kernel<R1, IV, IN16, EPI, WARPS, BF, STRIP>
-        <<<(unsigned)ctas, WARPS * 32, fast_smem_bytes<R1, EPI, WARPS, IV>(), stream>>>(plan->dev, a);
+        <<<(unsigned)ctas, WARPS * 32, fast_smem_bytes<R1, EPI, WARPS, IV, BF>(), stream>>>(plan->dev, a);
     SELD_CUDA_TRY(cudaGetLastError());
     return SELD_OK;
 }

@@ -11,16 +11,19 @@
 namespace seld {
 namespace tmem {
 
-constexpr int kCols = 512;  // the whole tensor memory of the SM: the feature kernels run one CTA per SM
-
+// Allocations are a power of two >= 32 columns (of the SM's 512); a kernel takes only what its tables need, so another
+// kernel's CTA that shares the SM (none fits next to the feature kernels' shared memory today) still finds columns.
 // warp-collective; `slot` is a shared-memory word that receives the base address
-__device__ __forceinline__ void alloc_all(uint32_t* slot) {
+template <int COLS>
+__device__ __forceinline__ void alloc(uint32_t* slot) {
+    static_assert(COLS >= 32 && COLS <= 512 && (COLS & (COLS - 1)) == 0, "tensor memory columns");
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(slot);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s), "n"(COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void dealloc_all(uint32_t base) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+template <int COLS>
+__device__ __forceinline__ void dealloc(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

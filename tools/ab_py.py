@@ -17,7 +17,9 @@ mean = torch.zeros((7, 64), device="cuda"); istd = torch.ones((7, 64), device="c
 plan = sb.features.get_plan(1024, 480, 64, 24000)
 T = plan.num_frames(x.shape[2])
 o32 = torch.empty((B, T, 7, 64), device="cuda"); o16 = torch.empty((B, 7, T, 64), device="cuda", dtype=torch.bfloat16)
+omic = torch.empty((B, T, 10, 64), device="cuda")
 cases = {
+  "mic f32": lambda: plan.run(x, mode="mic_gcc", out=omic),
   "foa f32": lambda: plan.run(x, mode="foa_iv", out=o32),
   "foa i16": lambda: plan.run(pcm, mode="foa_iv", out=o32),
   "foa bf16 ctf": lambda: plan.run(x, mode="foa_iv", mean=mean, inv_std=istd, layout="ctf", out_dtype=torch.bfloat16, out=o16),
