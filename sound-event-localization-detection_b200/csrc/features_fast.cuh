@@ -113,7 +113,12 @@ __device__ __forceinline__ float2 mul_fma_pair(float m0, float m1a, float m1b, f
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __device__ __forceinline__ float sample_of(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float sample_of(const short* p) { return (float)__ldg(p); }  // x 1/32768 lives in the window table
+// int16 -> float without the conversion unit (I2F runs at a quarter of the FP32 rate and cost the PCM kernel 13 %): the
+// integer 0x4B000000 + 32768 + x is the float 2^23 + 32768 + x, exactly, for every int16 x; one integer add, one float
+// add.  (x 1/32768 lives in the window table.)
+__device__ __forceinline__ float sample_of(const short* p) {
+    return __int_as_float((int)__ldg(p) + 0x4B008000) - 8421376.0f;
+}
 
 // edge frames (reflect padding, torch.stft center=True) and clips too short to be padded: rare, kept out of line
 template <int R1, class In>
