@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libseld_cuda.so")
+# SELD_CUDA_LIB: another build of the library (developer A/B runs, tools/build_variant.sh); the default is the in-tree one
+LIB_PATH = os.environ.get("SELD_CUDA_LIB") or os.path.join(_HERE, "libseld_cuda.so")
 
 SELD_MODE_LOGMEL, SELD_MODE_LOGMEL_IV, SELD_MODE_LOGMEL_GCC = 0, 1, 2
 SELD_DTYPE_F32, SELD_DTYPE_I16, SELD_DTYPE_BF16 = 0, 1, 2

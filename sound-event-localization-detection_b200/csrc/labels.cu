@@ -269,7 +269,10 @@ int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t
 // Nothing crosses PCIe and the host does no per-window work: the epoch's permutation, the window starts and the
 // per-window event ranges are resident in HBM.
 namespace seld {
-constexpr int kSliceRows = 5;
+#ifndef SELD_SLICE_ROWS
+#define SELD_SLICE_ROWS 5
+#endif
+constexpr int kSliceRows = SELD_SLICE_ROWS;
 
 __global__ void __launch_bounds__(256) loader_batch_kernel(
     const float4* __restrict__ feat, long long rows, int row_len4, const int* __restrict__ order, int first, int n_win,
