@@ -177,6 +177,25 @@ def test_pcm16_host_path_matches_float_path(sb):
     assert torch.equal(out_f, out_i)
 
 
+def test_pcm16_conversion_is_exact_for_every_value(sb):
+    """The kernel converts int16 with an integer add and a float add (0x4B008000 + x read as a float is 2^23 + 32768 + x):
+    every one of the 65536 values, the extremes included, must give what x / 32768 in float32 gives."""
+    from seld_b200.features import extract_features_host
+    allv = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
+    rng = np.random.default_rng(12)
+    pcm = rng.integers(-32768, 32768, size=(3, 4, 65536 + 480), dtype=np.int16)
+    for c in range(4):
+        pcm[0, c, :65536] = rng.permutation(allv)
+    pcm[1, 0, :4] = [-32768, 32767, 0, -1]
+    plan = sb.get_plan(1024, 480, 64, 24000, "cuda")
+    T = 1 + pcm.shape[2] // 480
+    out_i = torch.empty((3, T, 7, 64), dtype=torch.float32).pin_memory()
+    out_f = torch.empty_like(out_i).pin_memory()
+    extract_features_host(torch.from_numpy(pcm).pin_memory(), out_i, plan, mode="logmel_iv", chunk=2)
+    extract_features_host(torch.from_numpy(pcm.astype(np.float32) / 32768.0).pin_memory(), out_f, plan, mode="logmel_iv", chunk=2)
+    assert torch.equal(out_i, out_f)
+
+
 def test_v3_is_deterministic_and_configuration_independent(sb):
     """The two resource configurations of the fast kernel (12 warps x 168 registers, 8 warps x ~200 registers: different
     schedules, different numbers of groups per CTA) run the same arithmetic in the same order: bit-identical outputs,
