@@ -37,7 +37,11 @@
 //     of every lane, then an OR over all samples only if that test passes; BF: max == 0) and a (rare, warp-uniform)
 //     fix-up zeroes that channel's planes.
 //   * arithmetic is packed where the data come in pairs (add/sub/mul/fma.rn.f32x2 -> FADD2/FMUL2/FFMA2 on
-//     sm_100a): butterflies, window, channel split, power pairs.
+//     sm_100a): butterflies, complex multiplies, window, channel split, power pairs.
+//   * the lane's window row and pass-1 twiddle row (96 words every frame re-reads) live in TENSOR MEMORY
+//     (tmem_store.cuh): three LDTM.x32 per channel pair, issued ahead of the in-register DFT, instead of 24 LDS.128 — a
+//     fifth of the kernel's shared-memory wavefronts.  The block-floating variant keeps shared-memory tables (it has no
+//     registers to spare for the addresses and only runs over the redo list).
 #pragma once
 #include <cuda_bf16.h>
 

@@ -1,10 +1,12 @@
 // Tensor memory (TMEM, 256 KB per SM on sm_100a) used as a PER-LANE store: with the 32x32b access shape thread i of a
 // warp reads / writes `n` consecutive 32-bit columns of TMEM lane 32 * (warp % 4) + i — the same thread always sees the
-// same cells, nothing crosses lanes.  That is exactly the access pattern of
-//   * per-lane constant tables (window row, twiddle row of a lane) that every frame re-reads, and
-//   * values a lane parks and picks up again itself (the first channel pair's spectrum while the second is transformed),
-// which otherwise go through shared memory and its 128 B/clk datapath, the pipe that bounds the feature kernel
-// (DESIGN.md §3.1).  No tensor-core instruction is involved: tcgen05.alloc / st / ld / dealloc only.
+// same cells, nothing crosses lanes.  That is exactly the access pattern of the per-lane constant tables (window row,
+// twiddle row of a lane) that every frame of the feature kernel re-reads, and which otherwise go through shared memory
+// and its 128 B/clk datapath, the busiest pipe of that kernel.  No tensor-core instruction is involved:
+// tcgen05.alloc / st / ld / dealloc only.
+// Measured on B200: wide accesses pay (three LDTM.x32 for 24 LDS.128: -4 % kernel time); narrow ones do
+// not (x4 / x8 accesses for values a lane parks and picks up again: +14 %) — an access costs the SM about ten issue cycles
+// whatever its width, so only the x16 store (table set-up) and the x32 load are kept here.
 #pragma once
 #include <cstdint>
 
@@ -34,26 +36,6 @@ __device__ __forceinline__ uint32_t lane_base(uint32_t base, int warp) { return 
 
 // Loads are issued and completed in ONE asm statement (ld + wait::ld), so the compiler can never use a destination
 // register before the wait.  TMEM load latency is ~12 cycles, below a shared-memory load.
-__device__ __forceinline__ void ld4(uint32_t addr, float& a, float& b, float& c, float& d) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4]; tcgen05.wait::ld.sync.aligned;"
-                 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
-}
-__device__ __forceinline__ void st4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
-}
-__device__ __forceinline__ void ld8(uint32_t addr, float (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8]; tcgen05.wait::ld.sync.aligned;"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
-                 : "r"(addr));
-}
-__device__ __forceinline__ void ld16(uint32_t addr, float (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16]; "
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
-          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
-        : "r"(addr));
-}
 __device__ __forceinline__ void st16(uint32_t addr, const float (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -73,24 +55,6 @@ __device__ __forceinline__ void ld32(uint32_t addr, float (&r)[32]) {
 
 // Split form: the load is issued here and completed by ldN_wait(r) — code in between overlaps the TMEM access.  The wait
 // names every destination register as an in/out operand, so no use of r[] can be scheduled ahead of it.
-__device__ __forceinline__ void ld8_issue(uint32_t addr, float (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
-                 : "r"(addr));
-}
-__device__ __forceinline__ void ld8_wait(float (&r)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]));
-}
-__device__ __forceinline__ void ld16_issue(uint32_t addr, float (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
-                 : "r"(addr));
-}
-__device__ __forceinline__ void ld16_wait(float (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
-}
 __device__ __forceinline__ void ld32_issue(uint32_t addr, float (&r)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
