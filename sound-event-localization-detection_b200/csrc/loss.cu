@@ -167,6 +167,91 @@ __global__ void __launch_bounds__(256) class_loss_kernel(const float* __restrict
     }
 }
 
+// Tiled form of the same kernel (used when logits / grad are 16-byte aligned, i.e. always from torch): a CTA stages 256
+// cells = 3 584 floats through shared memory with coalesced 16-byte loads — one thread per cell reading its 14 logits
+// straight from global memory touches every 32-byte sector of the tile 8 times — computes from shared memory (a cell's
+// 14 floats as seven 8-byte loads: 56-byte pitch, conflict-free per half-warp) and, for the backward pass, writes the
+// gradient tile back in place and out with coalesced 16-byte stores.
+template <int M, int MODE, bool BWD>
+__global__ void __launch_bounds__(256, 4) class_loss_tiled_kernel(const float* __restrict__ logits,
+                                                               const unsigned short* __restrict__ mask, long long n_cells,
+                                                               const float* __restrict__ weight, double* __restrict__ sums,
+                                                               float* __restrict__ grad, const float* __restrict__ gscale) {
+    static_assert(M % 2 == 0, "cells are read as float2");
+    constexpr int TILE = 256, TW = TILE * M;
+    __shared__ __align__(16) float s_z[TW];
+    double acc = 0.0, wacc = 0.0;
+    const float gs = BWD ? *gscale : 0.f;
+    const long long n_tiles = (n_cells + TILE - 1) / TILE;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long c0 = tile * TILE;
+        const int nc = (int)min((long long)TILE, n_cells - c0);
+        const int nf = nc * M, nv = nf >> 2;
+        const float* src = logits + c0 * M;  // tile * 14 336 bytes: 16-byte aligned when logits is
+        for (int i = threadIdx.x; i < nv; i += TILE) reinterpret_cast<float4*>(s_z)[i] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+        for (int i = (nv << 2) + threadIdx.x; i < nf; i += TILE) s_z[i] = src[i];
+        __syncthreads();
+        if ((int)threadIdx.x < nc) {
+            float z[M], p[M], lse;
+            float2* zp = reinterpret_cast<float2*>(s_z + threadIdx.x * M);
+#pragma unroll
+            for (int k = 0; k < M / 2; ++k) {
+                const float2 t = zp[k];
+                z[2 * k] = t.x;
+                z[2 * k + 1] = t.y;
+            }
+            softmax_of<M>(z, p, lse);
+            unsigned y = mask[c0 + threadIdx.x];
+            if (y == 0u) y = 1u << (M - 1);  // untouched cell: one-hot background
+            float g[M];
+            if (MODE == 0) {
+                float se = 0.f, dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const float d = p[k] - ((y >> k) & 1u ? 1.f : 0.f);
+                    se = fmaf(d, d, se);
+                    dot = fmaf(d, p[k], dot);
+                }
+                acc += (double)se;
+                if (BWD) {
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        const float d = p[k] - ((y >> k) & 1u ? 1.f : 0.f);
+                        g[k] = gs * 2.f * p[k] * (d - dot);
+                    }
+                }
+            } else {
+                const int t = __ffs(y) - 1;
+                const float w = weight ? weight[t] : 1.f;
+                float zt = z[0];
+#pragma unroll
+                for (int k = 1; k < M; ++k) zt = k == t ? z[k] : zt;
+                acc += (double)(w * (lse - zt));
+                wacc += (double)w;
+                if (BWD) {
+#pragma unroll
+                    for (int k = 0; k < M; ++k) g[k] = gs * w * (p[k] - (k == t ? 1.f : 0.f));
+                }
+            }
+            if (BWD) {
+#pragma unroll
+                for (int k = 0; k < M / 2; ++k) zp[k] = make_float2(g[2 * k], g[2 * k + 1]);
+            }
+        }
+        if (BWD) {
+            __syncthreads();
+            float* dst = grad + c0 * M;
+            for (int i = threadIdx.x; i < nv; i += TILE) __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(s_z)[i]);
+            for (int i = (nv << 2) + threadIdx.x; i < nf; i += TILE) dst[i] = s_z[i];
+        }
+        __syncthreads();  // the next tile overwrites s_z
+    }
+    if (sums) {
+        block_add(acc, sums);
+        if (MODE == 1) block_add(wacc, sums + 1);
+    }
+}
+
 int launch_batch_class_mask(const int* order, int first, int n_win, const int* win_start, const int* win_lo, const int* win_hi,
                             int win_len, const int* events, const double* centres, int I, int J, int M, double sigma_az,
                             double sigma_el, unsigned short* mask, cudaStream_t st) {
@@ -193,6 +278,17 @@ int launch_class_loss(int mode, const float* logits, const unsigned short* mask,
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long blocks = (n_cells + 255) / 256;
+    const bool tiled = (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
+    if (tiled) {
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;  // 8 CTAs of 256 threads per SM, grid-stride over tiles
+#define SELD_LOSS_LAUNCH(MODE, BWD) \
+    class_loss_tiled_kernel<14, MODE, BWD><<<(unsigned)blocks, 256, 0, st>>>(logits, mask, n_cells, weight, sums, grad, gscale)
+        if (mode == 0) { if (grad) SELD_LOSS_LAUNCH(0, true); else SELD_LOSS_LAUNCH(0, false); }
+        else { if (grad) SELD_LOSS_LAUNCH(1, true); else SELD_LOSS_LAUNCH(1, false); }
+#undef SELD_LOSS_LAUNCH
+        SELD_CUDA_TRY(cudaGetLastError());
+        return SELD_OK;
+    }
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     if (mode == 0) class_loss_kernel<14, 0><<<(unsigned)blocks, 256, 0, st>>>(logits, mask, n_cells, weight, sums, grad, gscale);
     else class_loss_kernel<14, 1><<<(unsigned)blocks, 256, 0, st>>>(logits, mask, n_cells, weight, sums, grad, gscale);
