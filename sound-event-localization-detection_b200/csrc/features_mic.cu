@@ -28,7 +28,15 @@
 
 namespace seld {
 
-constexpr int kMicWarps = 8;  // per-warp shared memory ~25 KB (phasor park + 4 power planes + transpose tile)
+// 1: the unit phasors a lane parks for the inverse sweeps — (U0, U1) of pair a, (U2, U3) of pair b: 2 x 64 words per lane,
+//    written and read by the same lane — live in tensor memory (tmem_store.cuh, x32 accesses) instead of 8.3 KB of shared
+//    memory and 68 registers per warp; that is what lets the kernel run 12 warps x 168 registers instead of 8 x 255.
+#ifndef SELD_MIC_TMEM
+#define SELD_MIC_TMEM 1
+#endif
+constexpr bool kMicTm = SELD_MIC_TMEM != 0;
+constexpr int kMicWarps = kMicTm ? 12 : 8;  // per-warp shared memory: 17 KB (4 power planes + tile) | 25 KB (+ phasor park)
+constexpr int kMicTmCols = 512, kMicTmPitch = 128;  // per warp of a lane quarter: Q [16 bins x 4] at +0, (U2, U3) [16 x 4] at +64
 
 template <int R1>
 struct MicLayout {
@@ -36,7 +44,7 @@ struct MicLayout {
     using FL = FastLayout<R1>;
     static constexpr int NB = F::NB;
     static constexpr int PITCH = FL::PITCH;                  // power planes: same pitch / bank pattern as the FOA kernel
-    static constexpr int Q_WORDS = 4 * ((NB + 3) & ~3);      // float4 (U0.re, U0.im, U1.re, U1.im) per bin
+    static constexpr int Q_WORDS = kMicTm ? 0 : 4 * ((NB + 3) & ~3);  // float4 (U0.re, U0.im, U1.re, U1.im) per bin
     static constexpr int P_OFF = Q_WORDS;                    // 4 power planes P0..P3
     static constexpr int TILE_OFF = P_OFF + 4 * PITCH;
     static constexpr int TP = 34;                            // tile row pitch in float2 (17 x 16 B)
@@ -91,6 +99,16 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = warp >> 2, wi = warp & 3;
+    uint32_t tm_base = 0, tm_q = 0;  // tm_q: this warp's 128 columns (Q at +0, (U2, U3) at +64)
+    if constexpr (kMicTm) {
+        __shared__ uint32_t s_tm_slot;
+        if (warp == 0) tmem::alloc<kMicTmCols>(&s_tm_slot);
+        tmem::fence_before_sync();
+        __syncthreads();
+        tmem::fence_after_sync();
+        tm_base = s_tm_slot;
+        tm_q = tmem::lane_base(tm_base, warp) + kMicTmPitch * group;
+    }
     float* region = s_regions + warp * L::REGION;
     float* gregion = s_regions + (group * 4) * L::REGION;
     float4* Q = reinterpret_cast<float4*>(region);
@@ -105,7 +123,8 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
     const unsigned n_gitems = (n_items + 3u) >> 2;
     unsigned gidx = blockIdx.x * G + group;
     const unsigned gstride = gridDim.x * G;
-    if (gidx >= n_gitems) return;  // whole group leaves together
+    if (kMicTm ? false : gidx >= n_gitems) return;  // whole group leaves together (tensor-memory build: everybody meets at the end)
+    if (gidx < n_gitems) {
 
     const float* audio = reinterpret_cast<const float*>(a.audio);
     const int n_samples = (int)a.n_samples, hop = p.hop;
@@ -159,7 +178,7 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
         const bool more = gnext < n_gitems;
         const long long row_off = (((long long)cur.b * T_out + cur.t) * a.C_out + a.c_off) * 64;
         const bool row_ok = cur.flags & 2, row_exists = cur.flags & 1;
-        float4 U23[17];  // unit phasors (U2, U3) of this lane's bins lane + R1 kh (kh < 16) and of the Nyquist bin (lane 0)
+        float4 U23[kMicTm ? 1 : 17];  // unit phasors (U2, U3) of this lane's bins lane + R1 kh (kh < 16) and of the Nyquist bin (lane 0)
         unsigned silent = 0u;  // bit c: channel c is digitally silent in this frame
 
 #pragma unroll 1
@@ -259,25 +278,44 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
                 xb = make_float2(sS.y, -dD.x);
             };
             // per bin: scaled powers -> planes (2 pr, 2 pr + 1); unit phasors -> park (pair a) / registers (pair b)
+            float stg[32];  // tensor-memory build: unit phasors of eight bins, stored with one STTM.x32
             auto emit = [&](auto Slot, int k, float2 xa, float2 xb) {
+                constexpr int slot = decltype(Slot)::value;
                 const float pa = fmaf(xa.x, xa.x, xa.y * xa.y), pb = fmaf(xb.x, xb.x, xb.y * xb.y);
-                P[(2 * pr) * L::PITCH + k] = pa;
-                P[(2 * pr + 1) * L::PITCH + k] = pb;
+                if (active) {  // (tensor-memory build: lanes >= R1 come here with zeros for the warp-wide store below)
+                    P[(2 * pr) * L::PITCH + k] = pa;
+                    P[(2 * pr + 1) * L::PITCH + k] = pb;
+                }
                 const float2 ua2 = mic_unit(xa, pa, keep_a), ub2 = mic_unit(xb, pb, keep_b);
                 const float4 uu = make_float4(ua2.x, ua2.y, ub2.x, ub2.y);
-                if (pr == 0) Q[k] = uu;
-                else U23[decltype(Slot)::value] = uu;
+                if constexpr (kMicTm) {
+                    if constexpr (slot < 16) {
+                        stg[4 * (slot & 7)] = uu.x, stg[4 * (slot & 7) + 1] = uu.y, stg[4 * (slot & 7) + 2] = uu.z, stg[4 * (slot & 7) + 3] = uu.w;
+                    } else {  // the Nyquist bin (lane 0 only): two pad words of the pair's two planes, same thread reads them back
+                        pad(P, 2 * pr, 1) = uu.x, pad(P, 2 * pr, 2) = uu.y, pad(P, 2 * pr + 1, 1) = uu.z, pad(P, 2 * pr + 1, 2) = uu.w;
+                    }
+                } else {
+                    if (pr == 0) Q[k] = uu;
+                    else U23[slot] = uu;
+                }
             };
             static_for<16>([&](auto KH) {
+                constexpr int kh = decltype(KH)::value;
                 float2 xa, xb;
                 split(KH, xa, xb);
-                if (active) emit(KH, lane + R1 * decltype(KH)::value, xa, xb);
-                else if (pr == 1) U23[decltype(KH)::value] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (kMicTm) {
+                    // (lanes >= R1 of the 960 configuration transform zeros: their phasors are exact zeros)
+                    emit(KH, active ? lane + R1 * kh : 0, active ? xa : make_float2(0.f, 0.f), active ? xb : make_float2(0.f, 0.f));
+                    if constexpr ((kh & 7) == 7) tmem::st32(tm_q + 64 * pr + 32 * (kh >> 3), stg);
+                } else {
+                    if (active) emit(KH, lane + R1 * kh, xa, xb);
+                    else if (pr == 1) U23[kh] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             });
             {
                 const float2 z = cadd(u[16], u[16]);  // Nyquist bin: its own mirror -> X_a = (2 re, 0), X_b = (2 im, 0)
                 if (lane == 0) emit(std::integral_constant<int, 16>{}, NB - 1, make_float2(z.x, 0.f), make_float2(z.y, 0.f));
-                else if (pr == 1) U23[16] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else if (!kMicTm && pr == 1) U23[kMicTm ? 0 : 16] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (lane == 0) {  // factors of the two mel rows: block-floating un-scaling; 0 for a silent channel, whose packed
                               // spectrum is the partner's rounding noise (-> exactly -100 dB, like the reference's own FFT)
@@ -291,15 +329,51 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
         //  fully unrolled kernel was 168 KB of SASS and stalled on instruction fetch as soon as the audio streamed
         //  through L2 evicted its code)
         float* out_row = a.out + row_off + 4 * 64;
+        if constexpr (kMicTm) tmem::wait_st();
 #pragma unroll 1
         for (int S = 0; S < 3; ++S) {
             float2 w[32];
             auto build = [&](auto Sc) {
                 constexpr int SS = decltype(Sc)::value;
+                if constexpr (kMicTm) {
+                    // phasors come back from tensor memory eight bins at a time (2 x LDTM.x32); the Hermitian mirror of bin
+                    // (lane, kh) is register 31 - kh of lane R1 - lane — for lane 0 its own register 32 - kh, patched one step later
+                    static_for<2>([&](auto Hc) {
+                        constexpr int h = decltype(Hc)::value;
+                        float q[32], uq[32];
+                        tmem::ld32(tm_q + 32 * h, q);
+                        tmem::ld32(tm_q + 64 + 32 * h, uq);
+                        static_for<8>([&](auto Ic) {
+                            constexpr int i = decltype(Ic)::value, kh = 8 * h + i;
+                            float2 ga, gb;
+                            mic_pick<SS>(make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]),
+                                         make_float4(uq[4 * i], uq[4 * i + 1], uq[4 * i + 2], uq[4 * i + 3]), ga, gb);
+                            float2 g = make_float2(ga.x - gb.y, ga.y + gb.x);            // G_a + i G_b
+                            const float2 mir = make_float2(ga.x + gb.y, gb.x - ga.y);   // conj(G_a) + i conj(G_b) = bin N-k
+                            if (kh == 0) {  // lane 0 holds DC there: imaginary parts dropped like irfft
+                                g.x = lane == 0 ? ga.x : g.x;
+                                g.y = lane == 0 ? gb.x : g.y;
+                            }
+                            w[kh] = g;
+                            w[31 - kh] = make_float2(__shfl_sync(0xffffffffu, mir.x, src), __shfl_sync(0xffffffffu, mir.y, src));
+                            if constexpr (kh >= 1) {
+                                w[32 - kh].x = lane == 0 ? mir.x : w[32 - kh].x;
+                                w[32 - kh].y = lane == 0 ? mir.y : w[32 - kh].y;
+                            }
+                        });
+                    });
+                    if (lane == 0) {  // register 16 of lane 0: the Nyquist bin, real parts only (irfft ignores its imaginary part)
+                        float2 ga, gb;
+                        mic_pick<SS>(make_float4(pad(P, 0, 1), pad(P, 0, 2), pad(P, 1, 1), pad(P, 1, 2)),
+                                     make_float4(pad(P, 2, 1), pad(P, 2, 2), pad(P, 3, 1), pad(P, 3, 2)), ga, gb);
+                        w[16] = make_float2(ga.x, gb.x);
+                    }
+                    return;
+                }
                 float2 nyq = make_float2(0.f, 0.f);
                 if (lane == 0) {
                     float2 ga, gb;
-                    mic_pick<SS>(Q[NB - 1], U23[16], ga, gb);
+                    mic_pick<SS>(Q[NB - 1], U23[kMicTm ? 0 : 16], ga, gb);
                     nyq = make_float2(ga.x, gb.x);  // irfft ignores the imaginary part of the Nyquist bin
                 }
                 float2 mir[16];
@@ -307,7 +381,7 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
                     constexpr int kh = decltype(KH)::value;
                     const float4 q = Q[active ? lane + R1 * kh : 0];
                     float2 ga, gb;
-                    mic_pick<SS>(q, U23[kh], ga, gb);
+                    mic_pick<SS>(q, U23[kMicTm ? 0 : kh], ga, gb);
                     float2 g = make_float2(ga.x - gb.y, ga.y + gb.x);     // G_a + i G_b
                     mir[kh] = make_float2(ga.x + gb.y, gb.x - ga.y);      // conj(G_a) + i conj(G_b) = bin N-k
                     if (kh == 0) {  // lane 0 holds DC there: imaginary parts dropped like irfft
@@ -405,6 +479,12 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
     }
     group_barrier(bar_id);
     copy_out();
+    }  // gidx < n_gitems
+    if constexpr (kMicTm) {
+        tmem::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem::dealloc<kMicTmCols>(tm_base);
+    }
 }
 
 template <int R1>
