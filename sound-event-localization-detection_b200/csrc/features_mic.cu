@@ -7,10 +7,11 @@
 //
 // One warp per frame, groups of four warps for the mel phase, exactly like the FOA kernel (features_fast.cuh):
 //   pair a : window, block-floating level equalisation, packed FFT, split -> X0, X1; scaled powers -> planes P0, P1;
-//            unit phasors (U0, U1) parked per bin as one float4 (same lane reads them back: no synchronisation)
-//   pair b : the same -> P2, P3 planes; unit phasors (U2, U3) of the lane's 17 bins stay in REGISTERS
-//   3 sweeps: cross-spectrum phases of two microphone pairs {01,02}, {03,12}, {13,23} from (U0, U1) [one LDS.128 per bin]
-//            and (U2, U3) [registers], packed as G_a + i G_b with the Hermitian mirror bins fetched by one shuffle per
+//            unit phasors (U0, U1) of the lane's 16 bins parked in TENSOR MEMORY (64 words per lane, two STTM.x32; the
+//            same lane reads them back: no synchronisation; lane 0's Nyquist bin goes to four plane pad words)
+//   pair b : the same -> P2, P3 planes; unit phasors (U2, U3) -> 64 more tensor-memory words per lane
+//   3 sweeps: cross-spectrum phases of two microphone pairs {01,02}, {03,12}, {13,23} from (U0, U1) and (U2, U3) [four
+//            LDTM.x32 per sweep], packed as G_a + i G_b with the Hermitian mirror bins fetched by one shuffle per
 //            component, ONE inverse complex FFT whose real / imaginary parts are the two correlations: in-lane DFT-32 over
 //            k_hi, twiddle, transpose, second pass pruned to the two outputs that hold the lags [0, 31] and [-32, -1];
 //            128-byte coalesced stores straight from registers
@@ -21,9 +22,16 @@
 // |windowed sample| per channel, FMNMX3 + CREDUX); phases do not see the factor, the mel rows are un-scaled by it.
 // n_fft 1024 (R1 = 32) and 960 (R1 = 30, the reference's default config.py:85): for 960 the inverse runs over 30 lanes
 // with its own twiddle table W_960^(k_lo t_lo).
-// This kernel is bound by the FP32 pipe rather than by issue slots: the packed two-instruction complex multiply of
-// dft_inreg.cuh measured 3-7 % SLOWER here than the four scalar instructions (tools/mic_ab.sh), so it keeps the scalar form.
+// Round 2 first kept (U0, U1) in shared memory (8.3 KB per warp) and (U2, U3) in 68 registers per thread: 25 KB and 255
+// registers per warp allowed 8 warps per SM (9.4 ms per 256 x 60 s).  With both in tensor memory a warp needs 17 KB and 168
+// registers: 12 warps, 8.1 ms; the window / twiddle rows follow them there for n_fft 1024 (7.9 ms; 960 would need 544 of
+// the 512 columns).  -DSELD_MIC_TMEM=0 builds the shared-memory form.
+// The packed two-instruction complex multiply of dft_inreg.cuh (register pairs + uniform-register constants) measured
+// SLOWER here than the four scalar instructions — 3-7 % at 8 warps x 255 registers, 20 % at 12 warps x 168 (tools/mic_ab.py,
+// -DSELD_MIC_PACKED_CMUL=1) — so this kernel keeps the scalar form.
+#ifndef SELD_MIC_PACKED_CMUL
 #define SELD_SCALAR_CMUL
+#endif
 #include "features_fast.cuh"
 
 namespace seld {
@@ -35,6 +43,10 @@ namespace seld {
 #define SELD_MIC_TMEM 1
 #endif
 constexpr bool kMicTm = SELD_MIC_TMEM != 0;
+// 1: (n_fft 1024 only: 960 needs a second twiddle row and 544 > 512 columns) window and twiddle rows in tensor memory too
+#ifndef SELD_MIC_TMEM_TABLES
+#define SELD_MIC_TMEM_TABLES 1
+#endif
 constexpr int kMicWarps = kMicTm ? 12 : 8;  // per-warp shared memory: 17 KB (4 power planes + tile) | 25 KB (+ phasor park)
 constexpr int kMicTmCols = 512, kMicTmPitch = 128;  // per warp of a lane quarter: Q [16 bins x 4] at +0, (U2, U3) [16 x 4] at +64
 
@@ -99,7 +111,8 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = warp >> 2, wi = warp & 3;
-    uint32_t tm_base = 0, tm_q = 0;  // tm_q: this warp's 128 columns (Q at +0, (U2, U3) at +64)
+    constexpr bool TT = kMicTm && SELD_MIC_TMEM_TABLES != 0 && R1 == 32;
+    uint32_t tm_base = 0, tm_q = 0, tm_tab = 0;  // tm_q: this warp's 128 columns (Q at +0, (U2, U3) at +64)
     if constexpr (kMicTm) {
         __shared__ uint32_t s_tm_slot;
         if (warp == 0) tmem::alloc<kMicTmCols>(&s_tm_slot);
@@ -108,6 +121,32 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
         tmem::fence_after_sync();
         tm_base = s_tm_slot;
         tm_q = tmem::lane_base(tm_base, warp) + kMicTmPitch * group;
+        if constexpr (TT) {
+            tm_tab = tmem::lane_base(tm_base, warp) + 384;
+            if (warp < 4) {
+                float r[16];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = p.window[lane + 32 * (16 * c + i)];
+                    tmem::st16(tm_tab + 16 * c, r);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 t = p.twiddle[(8 * c + i) * 32 + lane];
+                        r[2 * i] = t.x;
+                        r[2 * i + 1] = t.y;
+                    }
+                    tmem::st16(tm_tab + 32 + 16 * c, r);
+                }
+                tmem::wait_st();
+            }
+            tmem::fence_before_sync();
+            __syncthreads();
+            tmem::fence_after_sync();
+        }
     }
     float* region = s_regions + warp * L::REGION;
     float* gregion = s_regions + (group * 4) * L::REGION;
@@ -183,27 +222,24 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
 
 #pragma unroll 1
         for (int pr = 0; pr < 2; ++pr) {
-            float4 wreg[(R1 + 3) / 4];
-            {
+            float wv[32];
+            if constexpr (TT) {
+                tmem::ld32_issue(tm_tab, wv);
+            } else {
                 const float4* wrow = reinterpret_cast<const float4*>(s_win + lane * 36);
 #pragma unroll
-                for (int i = 0; i < (R1 + 3) / 4; ++i) wreg[i] = wrow[i];
+                for (int i = 0; i < (R1 + 3) / 4; ++i) {
+                    const float4 w4 = wrow[i];
+                    wv[4 * i] = w4.x, wv[4 * i + 1] = w4.y, wv[4 * i + 2] = w4.z, wv[4 * i + 3] = w4.w;
+                }
             }
             if (pr == 0) {
                 group_barrier(bar_id);
                 copy_out();
             }
-            static_for<(R1 + 3) / 4>([&](auto Jq) {
-                constexpr int j0 = 4 * decltype(Jq)::value;
-                const float4 w4 = wreg[j0 / 4];
-                static_for<4>([&](auto Ji) {
-                    constexpr int j = j0 + decltype(Ji)::value;
-                    if constexpr (j < R1) {
-                        const float w = decltype(Ji)::value == 0 ? w4.x : decltype(Ji)::value == 1 ? w4.y : decltype(Ji)::value == 2 ? w4.z : w4.w;
-                        v[j] = cscale(v[j], w);
-                    }
-                });
-            });
+            if constexpr (TT) tmem::ld32_wait(wv);
+#pragma unroll
+            for (int j = 0; j < R1; ++j) v[j] = cscale(v[j], wv[j]);
             // block floating point (see features_fast.cuh, BF kernel)
             float ma[4] = {0.f, 0.f, 0.f, 0.f}, mb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -234,8 +270,20 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
             const float keep_a = sil_a ? 0.f : 1.f, keep_b = sil_b ? 0.f : 1.f;
             silent |= (sil_a ? 1u : 0u) << (2 * pr) | (sil_b ? 2u : 0u) << (2 * pr);
             float2 u[32];
-            Dft<R1, false>::run(v);
-            {
+            if constexpr (TT) {
+                float tw0[32], tw1[32];
+                tmem::ld32_issue(tm_tab + 32, tw0);
+                tmem::ld32_issue(tm_tab + 64, tw1);
+                Dft<R1, false>::run(v);
+                tmem::ld32_wait(tw0);
+                tmem::ld32_wait(tw1);
+                static_for<R1>([&](auto Kc) {
+                    constexpr int k = decltype(Kc)::value;
+                    if constexpr (k >= 1 && k < 16) v[k] = cmul(v[k], make_float2(tw0[2 * k], tw0[2 * k + 1]));
+                    if constexpr (k >= 16) v[k] = cmul(v[k], make_float2(tw1[2 * (k - 16)], tw1[2 * (k - 16) + 1]));
+                });
+            } else {
+                Dft<R1, false>::run(v);
                 const float4* trow = reinterpret_cast<const float4*>(s_tw + lane * 34);
                 static_for<(R1 + 1) / 2>([&](auto Kq) {
                     constexpr int k0 = 2 * decltype(Kq)::value;
@@ -405,8 +453,20 @@ __global__ void __launch_bounds__(kMicWarps * 32, 1) features_mic_kernel(PlanDev
             else if (S == 1) build(std::integral_constant<int, 1>{});
             else build(std::integral_constant<int, 2>{});
             // first pass (registers): inverse DFT-32 over k_hi, then the twiddle conj(W_N^(k_lo t_lo))
-            Dft<32, true>::run(w);
-            {
+            if constexpr (TT) {
+                float tw0[32], tw1[32];
+                tmem::ld32_issue(tm_tab + 32, tw0);
+                tmem::ld32_issue(tm_tab + 64, tw1);
+                Dft<32, true>::run(w);
+                tmem::ld32_wait(tw0);
+                tmem::ld32_wait(tw1);
+                static_for<32>([&](auto Kc) {
+                    constexpr int k = decltype(Kc)::value;
+                    if constexpr (k >= 1 && k < 16) w[k] = cmul_conj(w[k], make_float2(tw0[2 * k], tw0[2 * k + 1]));
+                    if constexpr (k >= 16) w[k] = cmul_conj(w[k], make_float2(tw1[2 * (k - 16)], tw1[2 * (k - 16) + 1]));
+                });
+            } else {
+                Dft<32, true>::run(w);
                 const float4* trow = reinterpret_cast<const float4*>(s_twi + lane * 34);
                 static_for<16>([&](auto Kq) {
                     constexpr int k0 = 2 * decltype(Kq)::value;
