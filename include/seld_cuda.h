@@ -217,6 +217,17 @@ SELD_API int seld_batch_class_mask(const int32_t* d_order, int first, int n_win,
 SELD_API int seld_class_loss(int loss_type, const float* d_logits, const uint16_t* d_mask, int64_t n_cells, int n_classes,
                     const float* d_class_weight, double* d_sums, float* d_grad, const float* d_grad_scale, void* stream);
 
+/* The reference loss's two dormant terms from the same compact targets (reference loss.py:56-88 aiur_loss, :90-146
+ * converging_localization_loss; both are commented out of SMRSELDLoss.forward, loss.py:158-165, and take softmax
+ * probabilities there — here the softmax of d_logits (n_frames, I*J, n_classes) is taken inside).
+ *   d_sums : float64[3], the call ADDS {sum over event frames and cells of p_nonbackground * y_at,  number of frames with
+ *            events,  sum over frames of the IoU of predicted and true event cells};
+ *            cl = sums[0] / (sums[1] * I * J + 1e-10), aiur = 1 - sums[2] / n_frames.  NULL = backward only.
+ *   d_grad : NULL, or (n_frames, I*J, n_classes) float32 <- d(sums[0])/d(logits) * (*d_grad_scale) (device scalar); the AIUR
+ *            term is an argmax statistic and has no gradient.      n_classes == 14, I*J <= 4096.                       */
+SELD_API int seld_aux_losses(const float* d_logits, const uint16_t* d_mask, int64_t n_frames, int I, int J, int n_classes,
+                    double* d_sums, float* d_grad, const float* d_grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

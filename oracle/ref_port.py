@@ -116,3 +116,36 @@ def class_ce_loss_port(y_pred: torch.Tensor, y_true: torch.Tensor, class_weights
     M = y_pred.shape[-1]
     target = torch.argmax(y_true, dim=-1).view(-1)
     return torch.nn.CrossEntropyLoss(weight=class_weights)(y_pred.reshape(-1, M), target)
+
+
+def aiur_loss_port(y_prob: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+    """loss.py:56-88: per frame, IoU between the cells whose most probable class is not the background (the last class) and
+    the cells whose target argmax is not the background; a frame with neither counts as IoU 1; 1 - mean IoU."""
+    bg = y_prob.shape[-1] - 1
+    pred = (y_prob.argmax(dim=-1) != bg).to(y_prob.dtype)
+    true = (y_true.argmax(dim=-1) != bg).to(y_prob.dtype)
+    inter = (pred * true).sum(dim=-1)
+    union = pred.sum(dim=-1) + true.sum(dim=-1) - inter
+    iou = torch.where(union > 0, inter / (union + 1e-8), torch.ones_like(inter))
+    return 1.0 - iou.mean()
+
+
+def cl_loss_port(y_prob: torch.Tensor, y_true: torch.Tensor, I: int, J: int, eps: float = 1e-10) -> torch.Tensor:
+    """loss.py:90-146 (eps = SMRSELDLoss.eps, loss.py:15): target map y' = 1 on background cells and -N_bac / (N_non + eps)
+    on event cells of a frame; y_at = y' + (sum over the 8 neighbours on the circular (I, J) grid of (neighbour - y')) / 8,
+    neighbours visited row by row from (-1, -1) to (1, 1); the loss is the sum over frames WITH events of
+    (probability of any event class) * y_at, over (number of such frames * I * J + eps)."""
+    B, T, G, M = y_prob.shape
+    act_true = y_true.view(B, T, I, J, M)[..., :-1].sum(dim=-1)
+    act_pred = y_prob.view(B, T, I, J, M)[..., :-1].sum(dim=-1)
+    n_bac = (act_true < 0.01).sum(dim=(2, 3), keepdim=True).to(y_prob.dtype)
+    n_non = (act_true > 0.01).sum(dim=(2, 3), keepdim=True).to(y_prob.dtype)
+    yp = torch.where(act_true > 0.01, (-(n_bac / (n_non + eps))).expand_as(act_true), torch.ones_like(act_true))
+    acc = torch.zeros_like(yp)
+    for di in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            if di or dj:
+                acc = acc + (torch.roll(yp, shifts=(-di, -dj), dims=(2, 3)) - yp)  # element (i, j) sees (i + di, j + dj)
+    y_at = yp + acc / 8.0
+    has = (n_non > 0).to(y_prob.dtype)
+    return ((act_pred * y_at) * has).sum() / (has.sum() * I * J + eps)

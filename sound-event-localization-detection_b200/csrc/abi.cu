@@ -60,6 +60,8 @@ int launch_pcm16_to_float(const short* in, float* out, long long n, cudaStream_t
 int launch_batch_class_mask(const int* order, int first, int n_win, const int* win_start, const int* win_lo, const int* win_hi,
                             int win_len, const int* events, const double* centres, int I, int J, int M, double sigma_az,
                             double sigma_el, unsigned short* mask, cudaStream_t st);
+int launch_aux_losses(const float* logits, const unsigned short* mask, long long n_frames, int I, int J, int M, double* sums,
+                      float* grad, const float* gscale, cudaStream_t st);
 int launch_class_loss(int mode, const float* logits, const unsigned short* mask, long long n_cells, int M, const float* weight,
                       double* sums, float* grad, const float* gscale, cudaStream_t st);
 int launch_loader_batch(const float* feat, long long rows, int row_len, const int* order, int first, int n_win,
@@ -73,7 +75,7 @@ using namespace seld;
 
 extern "C" {
 
-int seld_version(void) { return 200; }
+int seld_version(void) { return 201; }
 const char* seld_last_error(void) { return g_last_error.c_str(); }
 int64_t seld_num_frames(int64_t n_samples, int hop) { return hop > 0 ? 1 + n_samples / hop : 0; }
 int seld_out_channels(int mode, int n_channels) {
@@ -403,6 +405,17 @@ int seld_class_loss(int loss_type, const float* d_logits, const uint16_t* d_mask
     if (d_grad && !d_grad_scale) return bad_arg("seld_class_loss: d_grad needs d_grad_scale");
     SELD_GUARD_PTR(d_logits, "seld_class_loss");
     return launch_class_loss(loss_type, d_logits, d_mask, n_cells, n_classes, d_class_weight, d_sums, d_grad, d_grad_scale,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int seld_aux_losses(const float* d_logits, const uint16_t* d_mask, int64_t n_frames, int I, int J, int n_classes,
+                    double* d_sums, float* d_grad, const float* d_grad_scale, void* stream) {
+    if (n_frames < 0 || I < 1 || J < 1 || n_classes < 1) return bad_arg("seld_aux_losses: bad size");
+    if (n_frames == 0) return SELD_OK;
+    if (!d_logits || !d_mask || (!d_sums && !d_grad)) return bad_arg("seld_aux_losses: null pointer");
+    if (d_grad && !d_grad_scale) return bad_arg("seld_aux_losses: d_grad needs d_grad_scale");
+    SELD_GUARD_PTR(d_logits, "seld_aux_losses");
+    return launch_aux_losses(d_logits, d_mask, n_frames, I, J, n_classes, d_sums, d_grad, d_grad_scale,
                              static_cast<cudaStream_t>(stream));
 }
 

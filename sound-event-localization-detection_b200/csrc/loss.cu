@@ -252,6 +252,129 @@ __global__ void __launch_bounds__(256, 4) class_loss_tiled_kernel(const float* _
     }
 }
 
+// The two dormant terms of the reference's loss (loss.py:56-146; commented out of SMRSELDLoss.forward, loss.py:158-165) from
+// the same compact targets.  One CTA per frame (b, t); "event cell" = some class below the background class covers it
+// (mask & low bits != 0), which is both argmax(y_true) != M-1 (loss.py:66-71: the first maximum of a multi-hot row is its
+// lowest class) and sum(y_true[:-1]) > 0.01 (loss.py:113-118).
+//   AIUR (loss.py:56-88): IoU of {cells whose argmax prediction is not background} and {event cells} per frame
+//        (1 when both are empty), summed into sums[2].  argmax has no gradient.
+//   converging localisation (loss.py:90-146): y' = 1 on background cells, -N_bac / (N_non + 1e-10) on event cells; y_at =
+//        y' + mean over the 8 circular neighbours of (neighbour - y'), in the reference's summation order; the frame adds
+//        sum over cells of (1 - p_background as the sum of the 13 event probabilities) * y_at to sums[0] and 1 to sums[1]
+//        when it has events.  grad != null: d/d logits of that sum times (*gscale): y_at * p_k * ([k < M-1] - p_nonbg).
+template <int M>
+__global__ void __launch_bounds__(256) aux_loss_kernel(const float* __restrict__ logits, const unsigned short* __restrict__ mask,
+                                                       int I, int J, double* __restrict__ sums, float* __restrict__ grad,
+                                                       const float* __restrict__ gscale) {
+    extern __shared__ float s_f[];  // [cells] y', [cells] y_at
+    __shared__ int s_cnt[3];        // event cells | predicted event cells | both
+    const int cells = I * J;
+    float* s_y = s_f;
+    float* s_at = s_f + cells;
+    const long long f = blockIdx.x;
+    const unsigned short* mk = mask + f * cells;
+    const float* zf = logits + f * cells * M;
+    constexpr unsigned kEventBits = (1u << (M - 1)) - 1u;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int n_local = 0;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) n_local += (mk[c] & kEventBits) != 0u;
+    for (int o = 16; o > 0; o >>= 1) n_local += __shfl_down_sync(0xffffffffu, n_local, o);
+    if ((threadIdx.x & 31) == 0 && n_local) atomicAdd(&s_cnt[0], n_local);
+    __syncthreads();
+    const int n_non_i = s_cnt[0];
+    const float n_non = (float)n_non_i, n_bac = (float)(cells - n_non_i);
+    const float ratio = -(n_bac / (n_non + 1e-10f));
+    const bool has = n_non_i > 0;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) s_y[c] = (mk[c] & kEventBits) != 0u ? ratio : 1.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int i = c / J, j = c - i * J;
+        const float y = s_y[c];
+        float d = 0.f;
+#pragma unroll
+        for (int di = -1; di <= 1; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                if (di == 0 && dj == 0) continue;
+                const int ni = (i + di + I) % I, nj = (j + dj + J) % J;
+                d = __fadd_rn(d, __fsub_rn(s_y[ni * J + nj], y));
+            }
+        s_at[c] = __fadd_rn(y, __fdiv_rn(d, 8.0f));
+    }
+    __syncthreads();
+    const float gs = grad ? *gscale : 0.f;
+    double acc = 0.0;
+    int pc = 0, inter = 0;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        float z[M], p[M], lse;
+        const float2* zp = reinterpret_cast<const float2*>(zf + (long long)c * M);
+#pragma unroll
+        for (int k = 0; k < M / 2; ++k) {
+            const float2 t = zp[k];
+            z[2 * k] = t.x;
+            z[2 * k + 1] = t.y;
+        }
+        softmax_of<M>(z, p, lse);
+        float nonbg = 0.f, best = p[0];
+        int arg = 0;
+#pragma unroll
+        for (int k = 0; k < M - 1; ++k) nonbg += p[k];
+#pragma unroll
+        for (int k = 1; k < M; ++k)
+            if (p[k] > best) {
+                best = p[k];
+                arg = k;
+            }
+        const bool ev = (mk[c] & kEventBits) != 0u, pe = arg != M - 1;
+        pc += pe;
+        inter += pe && ev;
+        const float yat = s_at[c];
+        if (has) acc += (double)(nonbg * yat);
+        if (grad) {
+            const float gy = has ? gs * yat : 0.f;
+            float* gp = grad + (f * cells + c) * M;
+#pragma unroll
+            for (int k = 0; k < M; ++k)  // d/dz_k of sum_{m < M-1} p_m = p_k ([k < M-1] - p_nonbg); 1 - p_nonbg taken as p_background
+                gp[k] = gy * p[k] * (k < M - 1 ? p[M - 1] : -nonbg);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        pc += __shfl_down_sync(0xffffffffu, pc, o);
+        inter += __shfl_down_sync(0xffffffffu, inter, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (pc) atomicAdd(&s_cnt[1], pc);
+        if (inter) atomicAdd(&s_cnt[2], inter);
+    }
+    if (sums) {
+        block_add(acc, sums);  // (contains the __syncthreads that orders the counters above)
+        if (threadIdx.x == 0) {
+            const float uni = (float)(s_cnt[1] + n_non_i - s_cnt[2]);
+            const float iou = uni > 0.f ? (float)s_cnt[2] / (uni + 1e-8f) : 1.f;
+            atomicAdd(sums + 2, (double)iou);
+            if (has) atomicAdd(sums + 1, 1.0);
+        }
+    }
+}
+
+int launch_aux_losses(const float* logits, const unsigned short* mask, long long n_frames, int I, int J, int M, double* sums,
+                      float* grad, const float* gscale, cudaStream_t st) {
+    if (n_frames == 0) return SELD_OK;
+    if (M != 14) {
+        set_error("seld_aux_losses: compiled for the reference's 14 classes (config.py NUM_CLASSES)");
+        return SELD_ERR_UNSUPPORTED;
+    }
+    const long long cells = (long long)I * J;
+    if (cells < 1 || cells > 4096 || n_frames > 0x7fffffffll || (reinterpret_cast<uintptr_t>(logits) & 7) != 0) {
+        set_error("seld_aux_losses: needs 1 <= I * J <= 4096 cells, < 2^31 frames and 8-byte aligned logits");
+        return SELD_ERR_UNSUPPORTED;
+    }
+    aux_loss_kernel<14><<<(unsigned)n_frames, 256, 2 * cells * sizeof(float), st>>>(logits, mask, I, J, sums, grad, gscale);
+    SELD_CUDA_TRY(cudaGetLastError());
+    return SELD_OK;
+}
+
 int launch_batch_class_mask(const int* order, int first, int n_win, const int* win_start, const int* win_lo, const int* win_hi,
                             int win_len, const int* events, const double* centres, int I, int J, int M, double sigma_az,
                             double sigma_el, unsigned short* mask, cudaStream_t st) {

@@ -153,6 +153,38 @@ def csv_path(name: str) -> str:
     return os.path.join(CSV_DIR, LABEL_CASES[name][0])
 
 
+# ---- loss cases (reference loss.py): logits and dense targets from seeds ------------------------------------------------
+# name -> (B, T, I, J, events per frame, seed); frame 1 of every batch entry has no event at all, class 13 (the background
+# index) appears as an event class, cells collect several classes (multi-hot rows)
+LOSS_CASES = {"grid18x36": (2, 6, 18, 36, 7, 501), "grid6x12": (3, 5, 6, 12, 4, 502), "dense_events": (1, 4, 18, 36, 200, 503)}
+LOSS_M = 14
+
+
+def make_loss_case(name: str):
+    """(logits (B, T, I*J, 14) float32, dense targets (B, T, I*J, 14) float32 built like dataset.py:100-117, I, J)."""
+    B, T, I, J, n_ev, seed = LOSS_CASES[name]
+    rng = np.random.default_rng(seed)
+    G = I * J
+    z = (3.0 * rng.standard_normal((B, T, G, LOSS_M))).astype(np.float32)
+    y = np.zeros((B, T, G, LOSS_M), dtype=np.float32)
+    for b in range(B):
+        for t in range(T):
+            if t == 1:
+                continue
+            cells = rng.integers(0, G, size=n_ev)
+            cls = rng.integers(0, LOSS_M, size=n_ev)
+            y[b, t, cells, cls] = 1.0
+    y[..., LOSS_M - 1] = np.where(y.sum(-1) == 0, 1.0, y[..., LOSS_M - 1])  # cells without an event: one-hot background
+    return z, y, I, J
+
+
+def loss_mask(y: np.ndarray) -> np.ndarray:
+    """The int16 class-set mask of dense targets: bit c <=> y[..., c] == 1; 0 for a one-hot background row."""
+    bits = ((y != 0).astype(np.int64) << np.arange(y.shape[-1])).sum(-1)
+    bits = np.where(bits == (1 << (y.shape[-1] - 1)), 0, bits)
+    return bits.astype(np.uint16).view(np.int16)
+
+
 def pack_labels(labels: np.ndarray) -> np.ndarray:
     """{0,1} float32 (T, G, M) -> packed bits; caller asserts the value set first."""
     return np.packbits((np.asarray(labels) != 0).reshape(-1))

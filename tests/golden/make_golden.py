@@ -50,9 +50,42 @@ def import_reference():
     return dataset, smrl_seld_gaussian, utils
 
 
+def make_losses():
+    """losses.npz: the reference's SMRSELDLoss (loss.py) on the seeded cases of cases.LOSS_CASES — the live class losses
+    (loss.py:27-54) and the two dormant terms (aiur_loss :56-88, converging_localization_loss :90-146), float32 like the
+    trainer computes them, plus float64 runs of the same code as the accuracy yardstick."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_loss", os.path.join(REF, "loss.py"))
+    ref_loss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_loss)
+    out = {}
+    w = torch.from_numpy((np.random.default_rng(77).random(cases.LOSS_M) + 0.5).astype(np.float32))
+    out["ce_weights"] = w.numpy()
+    for name in cases.LOSS_CASES:
+        z, y, I, J = cases.make_loss_case(name)
+        for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            zt, yt = torch.from_numpy(z).to(dt), torch.from_numpy(y).to(dt)
+            crit = ref_loss.SMRSELDLoss("mse", grid_size=(I, J))
+            critw = ref_loss.SMRSELDLoss("ce", grid_size=(I, J), class_weights=w.to(dt))
+            p = torch.softmax(zt, dim=-1)  # what the commented-out lines of forward pass to the two terms (loss.py:158)
+            out[f"{name}/{tag}"] = np.array([float(crit.class_mse_loss(zt, yt)), float(crit.class_ce_loss(zt, yt)),
+                                             float(critw.class_ce_loss(zt, yt)), float(crit.aiur_loss(p, yt)),
+                                             float(crit.converging_localization_loss(p, yt))], dtype=np.float64)
+        if name == "grid6x12":  # the gradient of the differentiable dormant term, through the reference's own autograd
+            zt = torch.from_numpy(z).double().requires_grad_(True)
+            crit = ref_loss.SMRSELDLoss("mse", grid_size=(I, J))
+            crit.converging_localization_loss(torch.softmax(zt, dim=-1), torch.from_numpy(y).double()).backward()
+            out[f"{name}/cl_grad_f64"] = zt.grad.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
+    print("losses.npz:", len(out), "arrays")
+
+
 def main():
     torch.set_num_threads(1)
+    if "--only-losses" in sys.argv:
+        return make_losses()
     cases.write_csvs()
+    make_losses()
     dataset, gauss, utils = import_reference()
 
     # ---- features -------------------------------------------------------------------------

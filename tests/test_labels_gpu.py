@@ -1,6 +1,7 @@
 """GPU parity, bit-exact: label kernels (through the C ABI) against the golden outputs of the reference's
 metadata_to_labels / augment_with_gaussian_noise, the windowing of SELDDataset and the on-device loader."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -323,6 +324,47 @@ def test_compact_loss_equals_reference_loss_on_dense_labels(sb, gaussian):
             assert abs(breakdown[f"class_{loss_type}"] - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
             assert torch.allclose(total.double(), 2.5 * ref64, rtol=2e-6, atol=1e-9)
             assert torch.allclose(z2.grad, z1.grad, rtol=1e-4, atol=1e-12 + 1e-5 * float(z1.grad.abs().max()))
+
+
+def test_losses_from_masks_match_the_reference_golden_values(sb):
+    """All five loss terms of reference loss.py from logits + int16 class-set masks against the values the REAL reference
+    computed on dense targets (tests/golden/losses.npz): the live softmax-MSE / cross entropy / weighted cross entropy and
+    the dormant AIUR and converging-localisation terms (loss.py:56-146), incl. frames without events, class-13 events and
+    multi-hot cells; the converging-localisation gradient against the reference's autograd."""
+    from oracle import ref_port
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "losses.npz"))
+    w = torch.from_numpy(gold["ce_weights"]).cuda()
+    for name in cases.LOSS_CASES:
+        z, y, I, J = cases.make_loss_case(name)
+        zc = torch.from_numpy(z).cuda()
+        mask = torch.from_numpy(cases.loss_mask(y)).cuda()
+        want = gold[f"{name}/f64"]
+        for k, (lt, ww) in enumerate((("mse", None), ("ce", None), ("ce", w))):
+            crit = sb.CompactSMRSELDLoss(loss_type=lt, grid_size=(I, J), class_weights=ww)
+            _, br = crit(zc, mask)
+            assert abs(br[f"class_{lt}"] - want[k]) <= 2e-6 * abs(want[k]), (name, lt, br, want[k])
+        crit = sb.CompactSMRSELDLoss(loss_type="mse", w_class=1.5, w_aiur=0.25, w_cl=2.0, grid_size=(I, J), use_aux_terms=True)
+        z1 = zc.clone().requires_grad_(True)
+        total, br = crit(z1, mask)
+        assert abs(br["aiur"] - want[3]) <= 1e-6, (name, br["aiur"], want[3])
+        assert abs(br["cl"] - want[4]) <= 1e-5 * abs(want[4]) + 1e-9, (name, br["cl"], want[4])
+        assert abs(float(total) - (1.5 * want[0] + 0.25 * want[3] + 2.0 * want[4])) <= 1e-5
+        assert abs(float(crit.aiur_loss(zc, mask)) - want[3]) <= 1e-6
+        # gradient of the converging-localisation term alone
+        z2 = zc.clone().requires_grad_(True)
+        (3.0 * crit.converging_localization_loss(z2, mask)).backward()
+        z3 = torch.from_numpy(z).double().requires_grad_(True)
+        (3.0 * ref_port.cl_loss_port(torch.softmax(z3, dim=-1), torch.from_numpy(y).double(), I, J)).backward()
+        ref_g = z3.grad.float().cuda()
+        assert torch.allclose(z2.grad, ref_g, rtol=1e-4, atol=1e-6 * float(ref_g.abs().max()))
+        if name == "grid6x12":
+            gg = 3.0 * torch.from_numpy(gold["grid6x12/cl_grad_f64"]).cuda()
+            assert torch.allclose(z2.grad, gg, rtol=1e-4, atol=1e-6 * float(gg.abs().max()))
+        # the total's gradient = class part + w_cl * cl part (AIUR is an argmax statistic: no gradient)
+        total.backward()
+        z4 = zc.clone().requires_grad_(True)
+        sb.CompactSMRSELDLoss(loss_type="mse", w_class=1.5, grid_size=(I, J))(z4, mask)[0].backward()
+        assert torch.allclose(z1.grad, z4.grad + (2.0 / 3.0) * z2.grad, rtol=1e-4, atol=1e-9)
 
 
 def test_region_candidate_box_equals_exhaustive_test(sb):

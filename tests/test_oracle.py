@@ -2,6 +2,8 @@
 (tests/golden/make_golden.py) and against the notebook known-answers."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -190,3 +192,35 @@ def test_scaler_stats():
     c, s, ss = of.scaler_stats(f)
     mean, std = of.scaler_mean_std(c, s, ss)
     assert np.allclose(mean, f.reshape(100, -1).mean(0)) and np.allclose(std, f.reshape(100, -1).std(0))
+
+
+def test_loss_ports_reproduce_the_reference_losses():
+    """oracle/ref_port.py's restatements of reference loss.py (class losses :27-54, aiur_loss :56-88,
+    converging_localization_loss :90-146) against values the REAL reference produced (tests/golden/losses.npz, made by
+    make_golden.py): float32 runs agree to the last bits, the converging-localisation gradient through autograd."""
+    import torch
+    from oracle import ref_port
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "losses.npz"))
+    w = torch.from_numpy(gold["ce_weights"])
+    old = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        for name in cases.LOSS_CASES:
+            z, y, I, J = cases.make_loss_case(name)
+            zt, yt = torch.from_numpy(z), torch.from_numpy(y)
+            p = torch.softmax(zt, dim=-1)
+            got = [float(ref_port.class_mse_loss_port(zt, yt)), float(ref_port.class_ce_loss_port(zt, yt)),
+                   float(ref_port.class_ce_loss_port(zt, yt, w)), float(ref_port.aiur_loss_port(p, yt)),
+                   float(ref_port.cl_loss_port(p, yt, I, J))]
+            assert np.allclose(got, gold[f"{name}/f32"], rtol=1e-6, atol=1e-9), (name, got, gold[f"{name}/f32"])
+            # the mask the CUDA path consumes stands for exactly these targets
+            m = cases.loss_mask(y).view(np.uint16).astype(np.int64)
+            back = ((m[..., None] >> np.arange(cases.LOSS_M)) & 1).astype(np.float32)
+            back[..., cases.LOSS_M - 1] = np.where(m == 0, 1.0, back[..., cases.LOSS_M - 1])
+            assert np.array_equal(back, y), name
+        z, y, I, J = cases.make_loss_case("grid6x12")
+        zt = torch.from_numpy(z).double().requires_grad_(True)
+        ref_port.cl_loss_port(torch.softmax(zt, dim=-1), torch.from_numpy(y).double(), I, J).backward()
+        assert np.allclose(zt.grad.numpy(), gold["grid6x12/cl_grad_f64"], rtol=1e-5, atol=1e-9)
+    finally:
+        torch.set_num_threads(old)
