@@ -14,7 +14,9 @@ import torch
 logger = logging.getLogger("SMR_SELD")
 
 
-def read_wav(path: str):
+def read_wav(path: str, keep_pcm16: bool = False):
+    """(channels, samples) float32 in [-1, 1) and the sample rate.  ``keep_pcm16``: a 16-bit PCM file comes back as the
+    int16 samples themselves (the feature kernel converts them while loading, x / 32768 exactly like here)."""
     with open(path, "rb") as f:
         data = f.read()
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
@@ -37,6 +39,8 @@ def read_wav(path: str):
     n = len(pcm) // (ch * bits // 8)
     pcm = pcm[: n * ch * bits // 8]
     if tag == 1:
+        if bits == 16 and keep_pcm16:
+            return np.ascontiguousarray(np.frombuffer(pcm, dtype="<i2").reshape(n, ch).T), sr
         if bits == 16:
             x = np.frombuffer(pcm, dtype="<i2").astype(np.float32) / 32768.0
         elif bits == 32:
@@ -72,6 +76,17 @@ def load_audio(audio_path):
     """Drop-in for reference dataset.py:18-25: returns (float32 tensor (channels, samples), sample_rate) and
     warns when the file does not have 4 channels."""
     x, sr = read_wav(str(audio_path))
+    waveform = torch.from_numpy(x)
+    if waveform.shape[0] != 4:
+        logger.warning(f"Expected 4 channels but got {waveform.shape[0]} channels in {audio_path}")
+    return waveform, sr
+
+
+def load_audio_pcm16(audio_path):
+    """Ingest form of ``load_audio`` used by ``SELDDataset``: 16-bit PCM files — the STARSS sets — stay
+    int16 ``(channels, samples)``, half the bytes over PCIe and no float pass on the host; the feature kernel divides by
+    32768 while loading, bit-identical to ``load_audio``'s result.  Other encodings come back as float32 like ``load_audio``."""
+    x, sr = read_wav(str(audio_path), keep_pcm16=True)
     waveform = torch.from_numpy(x)
     if waveform.shape[0] != 4:
         logger.warning(f"Expected 4 channels but got {waveform.shape[0]} channels in {audio_path}")

@@ -15,6 +15,7 @@ B200-first differences (none visible through the reference API):
 from __future__ import annotations
 
 import logging
+import os
 from glob import glob
 from pathlib import Path
 
@@ -23,7 +24,7 @@ import torch
 from torch.utils.data import Dataset
 
 from . import _lib, labels as L
-from .audio_io import load_audio  # noqa: F401  (re-exported like the reference's dataset.load_audio)
+from .audio_io import load_audio, load_audio_pcm16  # noqa: F401  (load_audio re-exported like the reference's dataset.load_audio)
 from .config import get_config
 from .features import audio_to_mel_spectrogram, get_plan  # noqa: F401
 from .labels import augment_with_gaussian_noise, metadata_to_labels, polar_to_grid  # noqa: F401
@@ -172,7 +173,8 @@ class SELDDataset(Dataset):
         self.feature_type = feature_type or getattr(config, "FEATURE_TYPE", "logmel")
         self._mode = FEATURE_MODES[self.feature_type]
         self.device = L._cuda_device(device)
-        self._load_audio = audio_loader or load_audio
+        # default ingest keeps 16-bit PCM files as int16 (converted inside the feature kernel); a custom loader may return either
+        self._load_audio = audio_loader or load_audio_pcm16
         self._compute_stats = compute_stats
         # distributed=True: ``audio_files`` is this rank's contiguous block of the global list (``shard_files``); windows
         # are those of the GLOBAL concatenation that start in the block, bit-identical to the unsharded dataset's — the
@@ -199,9 +201,16 @@ class SELDDataset(Dataset):
         logger.info("Loading and processing all audio files...")
         waves, per_file = [], []
         total = 0
+        # files are read and decoded by a few threads (file I/O and numpy release the GIL) while this thread parses the
+        # metadata in file order — the Gaussian label noise draws from numpy's global RNG in that order
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) // 2)))
+        pending = [pool.submit(self._load_audio, a) for a in self.audio_files]
+        pool.shutdown(wait=False)
         for idx, (audio_path, metadata_path) in enumerate(zip(self.audio_files, self.metadata_files)):
             try:
-                waveform, sr = self._load_audio(audio_path)
+                waveform, sr = pending[idx].result()
+                pending[idx] = None
                 audio_duration = waveform.shape[1] / sr
                 if self.use_gaussian_augmentation:
                     events, centres, t_lab = L.region_events(metadata_path, audio_duration, self.I, self.J,
@@ -234,7 +243,9 @@ class SELDDataset(Dataset):
         self.file_frames = [p[1] for p in per_file]
         feats = None
         stats = None
-        for (waveform, sr), (off, keep, _ev, _ce) in zip(waves, per_file):
+        for i, (off, keep, _ev, _ce) in enumerate(per_file):
+            waveform, sr = waves[i]
+            waves[i] = None  # the host copy is released as soon as the file is on its way to the GPU
             if plan is None or plan.sample_rate != sr:
                 plan = get_plan(self.n_fft, self.spectrogram_hop_length, self.n_mels, sr, dev)
             c_out = plan.out_channels(_lib_mode(self._mode), waveform.shape[0])
@@ -247,8 +258,12 @@ class SELDDataset(Dataset):
                 raise RuntimeError(f"Sizes of tensors must match: {c_out} feature channels vs {n_ch}")
             if keep == 0:
                 continue
-            x = waveform.to(device=dev, dtype=torch.float32, non_blocking=True).unsqueeze(0)
-            plan.run(x, mode=self._mode, out=feats[off:off + keep].unsqueeze(0), T_out=keep, stats=stats)
+            x = waveform.to(device=dev, non_blocking=True)
+            if x.dtype == torch.int16 and not (plan.fast and x.shape[0] == 4 and self._mode != "logmel_gcc"):
+                x = x.to(torch.float32) * (1.0 / 32768.0)  # outside the fast kernel's configurations: exact, on the device
+            elif x.dtype != torch.int16:
+                x = x.to(torch.float32)
+            plan.run(x.unsqueeze(0), mode=self._mode, out=feats[off:off + keep].unsqueeze(0), T_out=keep, stats=stats)
         if feats is None:
             raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")
         self.n_channels = n_ch

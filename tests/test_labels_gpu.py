@@ -326,6 +326,26 @@ def test_compact_loss_equals_reference_loss_on_dense_labels(sb, gaussian):
             assert torch.allclose(z2.grad, z1.grad, rtol=1e-4, atol=1e-12 + 1e-5 * float(z1.grad.abs().max()))
 
 
+def test_dataset_ingests_pcm16_wav_files_without_a_host_float_pass(sb, tmp_path):
+    """SELDDataset's default loader keeps 16-bit PCM WAV files as int16 (half the PCIe bytes, files read by a thread pool);
+    the kernel's x / 32768 is exact, so features, labels and windows equal those of the float32 ``load_audio`` path bit for
+    bit — for the FOA, log-mel and MIC (converted on the device: the MIC kernel takes float32) feature types."""
+    files, csvs = [], []
+    for i, (n, seed, csv) in enumerate(((97440, 41, "edges"), (60000, 42, "floatcol"), (48480, 43, "weird"))):
+        p = tmp_path / f"clip{i}.wav"
+        sb.audio_io.write_wav_pcm16(str(p), cases.make_audio("int16", n, seed), cases.SR)
+        files.append(str(p))
+        csvs.append(cases.csv_path(csv))
+    for ft in ("foa_iv", "logmel", "mic_gcc"):
+        a = sb.SELDDataset(files, csvs, resident="cuda", labels="compact", feature_type=ft)
+        b = sb.SELDDataset(files, csvs, resident="cuda", labels="compact", feature_type=ft, audio_loader=sb.load_audio)
+        assert len(a) == len(b) and a.total_frames == b.total_frames
+        assert torch.equal(a._features_tcf, b._features_tcf), ft
+        for k in (0, len(a) - 1):
+            (sa, la), (sb_, lb) = a[k], b[k]
+            assert torch.equal(sa, sb_) and torch.equal(la, lb)
+
+
 def test_losses_from_masks_match_the_reference_golden_values(sb):
     """All five loss terms of reference loss.py from logits + int16 class-set masks against the values the REAL reference
     computed on dense targets (tests/golden/losses.npz): the live softmax-MSE / cross entropy / weighted cross entropy and

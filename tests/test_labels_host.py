@@ -2,6 +2,7 @@
 vectors of the real reference.  The dense painting itself runs on the GPU (tests/test_labels_gpu.py); here the
 compact events are expanded by a few lines of numpy so the host logic is covered without a device."""
 import numpy as np
+import torch
 import pytest
 
 import cases
@@ -114,3 +115,7 @@ def test_wav_roundtrip(tmp_path):
     y, sr = seld_b200.load_audio(str(p))
     assert sr == 24000 and y.shape == (4, 4800) and y.dtype.is_floating_point
     assert np.array_equal(y.numpy(), x)  # int16-quantised input survives exactly (value / 32768)
+    # the dataset's ingest form keeps the int16 samples (converted inside the feature kernel)
+    z, sr2 = seld_b200.audio_io.load_audio_pcm16(str(p))
+    assert sr2 == 24000 and z.dtype == torch.int16 and z.shape == (4, 4800)
+    assert np.array_equal(z.numpy().astype(np.float32) / 32768.0, x)
