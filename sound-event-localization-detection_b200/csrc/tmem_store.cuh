@@ -1,12 +1,14 @@
 // Tensor memory (TMEM, 256 KB per SM on sm_100a) used as a PER-LANE store: with the 32x32b access shape thread i of a
 // warp reads / writes `n` consecutive 32-bit columns of TMEM lane 32 * (warp % 4) + i — the same thread always sees the
-// same cells, nothing crosses lanes.  That is exactly the access pattern of the per-lane constant tables (window row,
-// twiddle row of a lane) that every frame of the feature kernel re-reads, and which otherwise go through shared memory
-// and its 128 B/clk datapath, the busiest pipe of that kernel.  No tensor-core instruction is involved:
-// tcgen05.alloc / st / ld / dealloc only.
-// Measured on B200: wide accesses pay (three LDTM.x32 for 24 LDS.128: -4 % kernel time); narrow ones do
-// not (x4 / x8 accesses for values a lane parks and picks up again: +14 %) — an access costs the SM about ten issue cycles
-// whatever its width, so only the x16 store (table set-up) and the x32 load are kept here.
+// same cells, nothing crosses lanes.  That is exactly the access pattern of
+//   * the per-lane constant tables (window row, twiddle row of a lane) that every frame of the feature kernels re-reads and
+//     that otherwise go through shared memory and its 128 B/clk datapath, the busiest pipe of the FOA kernel;
+//   * the unit phasors a lane of the MIC kernel writes once per frame and reads back three times: out of
+//     shared memory and registers they are what lets that kernel run 12 warps per SM instead of 8.
+// No tensor-core instruction is involved: tcgen05.alloc / st / ld / dealloc only.
+// Measured on B200: wide accesses to read-only tables fetched ahead of independent work pay (three LDTM.x32 for 24 LDS.128:
+// -4 % FOA kernel time); narrow ones do not (x4 / x8: +14 %), and neither do loads on a dependent path that buy no
+// occupancy (the FOA kernel's parked spectrum with x32 / x16 accesses: +8.7 %).
 #pragma once
 #include <cstdint>
 
@@ -34,8 +36,8 @@ __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.
 // address of column `col` in this warp's 32 lanes
 __device__ __forceinline__ uint32_t lane_base(uint32_t base, int warp) { return base + ((uint32_t)(32 * (warp & 3)) << 16); }
 
-// Loads are issued and completed in ONE asm statement (ld + wait::ld), so the compiler can never use a destination
-// register before the wait.  TMEM load latency is ~12 cycles, below a shared-memory load.
+// Stores complete at the next wait_st(); loads are issued and completed in ONE asm statement (ld + wait::ld), so the
+// compiler can never use a destination register before the wait.
 __device__ __forceinline__ void st16(uint32_t addr, const float (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
